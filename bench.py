@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — raw-pixel GB/s of the encode+decode hot path (BASELINE.json `metric`).
+
+A step = one encode pass + one decode pass over one batch of synthetic images.
+  value : whole-job raw-pixel GB/s, inputs resident in HBM, CUDA-event timed.
+  e2e   : the same metric through the host-buffer C-ABI calls (pinned host memory in, host
+          memory out; H2D and D2H inside the timed region).
+  roofline / kernels : per-kernel CUDA-event durations from the library's timing hook,
+          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline : the scalar CPU model of the same provisional format on the host cores.
+
+LICENSING GATE: the reference may not be built, run or restated (LICENSING.md), so
+`--impl reference` reports it unavailable; the CPU figures printed are for the FLP0 CPU
+model in oracle/, which is NOT the reference.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "raw_pixel_GBps_encode_plus_decode"
+GATE = ("licensing gate: reference README reserves all use, no licence file; BASELINE.json north_star forbids "
+        "building/running/restating it until cleared (LICENSING.md); no Rust toolchain in the image either")
+
+# workload name -> (config id, images per GPU per step)
+WORKLOADS = {
+    "C2x64": ("C2", 64),  # configs[1] geometry (3840x2160 RGBA8) batched so a step exceeds L2 (2.1 GB raw)
+    "C1": ("C1", 1), "C2": ("C2", 1), "C3": ("C3", 128), "C4": ("C4", 1), "C5": ("C5", 64),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if mx and x > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_model_roundtrip(batch, seconds=20.0):
+    """Scalar CPU model (oracle/) encode+decode on all host cores over a bounded sample of the batch."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle_binding
+    so = os.path.join(ROOT, "oracle", "libflp0_oracle.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    orc = oracle_binding.Oracle(so)
+    cores = os.cpu_count() or 1
+    per_img = batch[0].nbytes
+    # ~80 MB/s round trip per core: size the sample to about `seconds` of work
+    k = int(max(cores, min(100000, seconds * 80e6 * cores / per_img)))
+    idx = [i % len(batch) for i in range(k)]
+
+    def one(i):
+        s = orc.encode(batch[i])
+        out = orc.decode(s, batch[i].shape)
+        return s.size, bool(np.array_equal(out, batch[i]))
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:  # ctypes releases the GIL
+        res = list(ex.map(one, idx))
+    dt = time.perf_counter() - t0
+    assert all(ok for _, ok in res)
+    return {"value": k * per_img / dt / 1e9, "unit": "GB/s", "cores": min(cores, k),
+            "kind": "provisional-format-cpu-model",
+            "sample": f"{k} images of {batch.shape[2]}x{batch.shape[1]}x{batch.shape[3]} encode+decode, "
+                      f"{min(cores, k)} threads, {dt:.1f} s; scalar C model of FLP0 (oracle/), NOT the gated reference"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import flic_b200
+    cfg, n = WORKLOADS[args.workload]
+    line = {"impl": "reference", "unavailable": GATE, "metric": METRIC, "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "config": {"workload": args.workload}}
+    try:  # the only CPU number that exists: the FLP0 model, clearly not the reference
+        batch = flic_b200.workloads.make_batch(cfg, n=min(n, 8))
+        line["flp0_cpu_model"] = cpu_model_roundtrip(batch, seconds=15.0)
+    except Exception as e:  # pragma: no cover
+        line["flp0_cpu_model"] = {"error": repr(e)}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2x64", choices=sorted(WORKLOADS))
+    ap.add_argument("--flags", type=lambda s: int(s, 0), default=0x01)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import flic_b200
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    flic_b200.build_library()
+    codec = flic_b200.Codec(local)
+
+    cfg, n = WORKLOADS[args.workload]
+    # weak scaling: every rank owns its own `n` images (independent units, no data-path collective)
+    batch = flic_b200.workloads.make_batch(cfg, n=n)
+    _, h, w, c = batch.shape
+    raw = batch.nbytes
+    host_px = torch.from_numpy(batch).pin_memory()
+    px = host_px.cuda(non_blocking=True)
+    cap = n * flic_b200.max_stream_bytes(w, h, c)
+    streams = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    out = torch.empty_like(px)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if raw < (512 << 20) else None
+    st = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        codec.encode_batch_device(px, streams, off, args.flags, st)
+        codec.decode_batch_device(streams, off, out, args.flags, st)
+
+    for _ in range(args.warmup):
+        step()
+    codec.check(st)
+    assert torch.equal(out, px), "round trip is not lossless"
+    comp = int(off[-1].item())
+    r = comp / raw
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, per-step events (L2 flush between steps is outside them) ----
+    codec.kernel_times()
+    codec.set_kernel_timing(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = codec.launches
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    for a, m, b in ev:
+        if flush is not None:
+            flush.fill_(1)
+        a.record()
+        codec.encode_batch_device(px, streams, off, args.flags, st)
+        m.record()
+        codec.decode_batch_device(streams, off, out, args.flags, st)
+        b.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = codec.launches - launches0
+    codec.set_kernel_timing(False)
+    ktimes = codec.kernel_times()
+    codec.check(st)
+    enc_ms = sum(a.elapsed_time(m) for a, m, _ in ev)
+    dec_ms = sum(m.elapsed_time(b) for _, m, b in ev)
+    tot = torch.tensor([enc_ms + dec_ms, enc_ms, dec_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    tot_ms, enc_ms, dec_ms = (float(x) for x in tot.tolist())
+    ms_per_step = tot_ms / args.steps
+    value = world * raw / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer ABI: pinned host pixels in, host pixels out ----
+    e2e = None
+    if not args.no_e2e:
+        h_streams = torch.empty(cap, dtype=torch.uint8).pin_memory().numpy()
+        h_off = np.zeros(n + 1, dtype=np.uint64)
+        h_out = torch.empty_like(host_px).pin_memory().numpy()
+        h_in = host_px.numpy()
+
+        def e2e_step():
+            s, o = codec.encode_batch(h_in, args.flags, out=h_streams, offsets=h_off)
+            codec.decode_batch(s, o, out=h_out)
+            return s.size
+
+        for _ in range(2):
+            e2e_step()
+        assert np.array_equal(h_out, h_in)
+        k = max(3, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            nbytes = e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * raw * k / float(dt) / 1e9, "unit": "GB/s", "steps": k,
+               "h2d_bytes_per_step": int(raw + nbytes + 8 * (n + 1)), "d2h_bytes_per_step": int(nbytes + raw + 8 * (n + 1) + 8),
+               "note": "flic_encode_batch + flic_decode_batch on pinned host buffers; host wall clock, max over ranks"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, peak_src = peaks()
+    alg = {"k_histograms": raw, "k_tables": 0, "k_pack": raw + comp, "k_finalize": 0, "k_decode": raw + comp}
+    kernels = {}
+    for k, (ms, cnt) in ktimes.items():
+        if cnt:
+            avg = ms / cnt
+            kernels[k] = {"avg_ms": round(avg, 4), "launches": cnt, "share_of_step": round(ms / tot_ms, 4),
+                          "alg_GBps": round(alg[k] / (avg * 1e-3) / 1e9, 1) if alg[k] else None}
+    dom = max(kernels, key=lambda k: kernels[k]["avg_ms"]) if kernels else None
+    roof = None
+    if dom:
+        ach = alg[dom] / (kernels[dom]["avg_ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
+                "frac": round(ach / hbm, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom],
+                "encode_path_frac": round((raw + comp) / (enc_ms / args.steps * 1e-3) / 1e9 / hbm, 4),
+                "decode_path_frac": round((raw + comp) / (dec_ms / args.steps * 1e-3) / 1e9 / hbm, 4)}
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "images_per_gpu": n, "width": w, "height": h, "channels": c,
+                   "raw_bytes_per_gpu_step": raw, "flags": args.flags,
+                   "l2": "inputs_exceed_l2" if flush is None else "l2_flushed_between_steps",
+                   "format": "FLP0 (provisional; NOT the reference bitstream — licensing gate)"},
+        "encode_GBps": round(world * raw / (enc_ms / args.steps * 1e-3) / 1e9, 2),
+        "decode_GBps": round(world * raw / (dec_ms / args.steps * 1e-3) / 1e9, 2),
+        "compressed_ratio": round(r, 4), "bits_per_pixel": round(8 * comp / (n * w * h), 3),
+        "parity": "byte-exact vs FLP0 CPU model (tests/); vs reference: unpinned — licensing gate",
+        "roofline": roof, "kernels": kernels, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_model_roundtrip(batch, seconds=20.0)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,400 @@
+// api.cu — C ABI of libflicb200.so (include/flic_b200.h): context, workspace,
+// device-resident and host-buffer batch entry points, header parsing and the
+// block-row splice.  Host logic only; every byte of codec work happens in the
+// kernels of encode.cu / decode.cu.  There is no CPU fallback anywhere here.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace flic;
+
+struct flic_ctx {
+    int device = 0;
+    char msg[256] = {0};
+    uint64_t launches = 0;
+    // per-block workspace (grown on demand)
+    uint64_t ws_blocks = 0;
+    uint16_t *d_hist = nullptr, *d_table = nullptr;
+    unsigned long long *d_status = nullptr, *d_dirE = nullptr;
+    uint32_t *d_err = nullptr;
+    uint32_t *h_err = nullptr;  // pinned
+    // host-API staging (grown on demand)
+    uint8_t *d_pix = nullptr, *d_str = nullptr;
+    unsigned long long *d_off = nullptr;
+    uint64_t pix_cap = 0, str_cap = 0, off_cap = 0;
+    unsigned long long *h_off = nullptr;  // pinned, off_cap entries
+    cudaStream_t stream = nullptr;        // used by the host-buffer API
+    // opt-in per-kernel timing (flic_set_kernel_timing): event pairs recorded on the launching stream
+    bool timing = false;
+    struct Span { cudaEvent_t a, b; int kernel; };
+    std::vector<Span> spans;      // recorded, not yet read
+    std::vector<Span> free_spans; // recycled events
+};
+
+namespace {
+// Brackets one kernel launch with events when timing is on; a no-op otherwise.
+struct KernelTimer {
+    flic_ctx *ctx; cudaStream_t s; flic_ctx::Span sp; bool on;
+    KernelTimer(flic_ctx *c, int kernel, cudaStream_t st) : ctx(c), s(st), on(c->timing) {
+        if (!on) return;
+        if (!ctx->free_spans.empty()) { sp = ctx->free_spans.back(); ctx->free_spans.pop_back(); }
+        else if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) { on = false; return; }
+        sp.kernel = kernel;
+        cudaEventRecord(sp.a, s);
+    }
+    ~KernelTimer() {
+        if (!on) return;
+        cudaEventRecord(sp.b, s);
+        ctx->spans.push_back(sp);
+    }
+};
+}  // namespace
+
+static int cuda_fail(flic_ctx *ctx, cudaError_t e, const char *what) {
+    if (ctx) snprintf(ctx->msg, sizeof ctx->msg, "%s: %s", what, cudaGetErrorString(e));
+    return FLIC_E_CUDA;
+}
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);   \
+    } while (0)
+
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+extern "C" int flic_version(void) { return 1; }
+
+extern "C" const char *flic_strerror(int code) {
+    switch (code) {
+        case FLIC_OK: return "ok";
+        case FLIC_E_ARG: return "invalid argument";
+        case FLIC_E_CAPACITY: return "output buffer too small";
+        case FLIC_E_FORMAT: return "malformed stream";
+        case FLIC_E_CUDA: return "CUDA error";
+        case FLIC_E_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
+        case FLIC_E_UNSUPPORTED: return "unsupported format feature";
+        case FLIC_E_INTERNAL: return "device-side consistency check failed";
+        default: return "unknown error";
+    }
+}
+
+extern "C" const char *flic_last_error(const flic_ctx *ctx) { return ctx ? ctx->msg : ""; }
+extern "C" uint64_t flic_launch_count(const flic_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" uint64_t flic_blocks_per_image(uint32_t w, uint32_t h) {
+    return (uint64_t)cdiv(w, kBW) * cdiv(h, kBH);
+}
+
+extern "C" uint64_t flic_max_stream_bytes(uint32_t w, uint32_t h, uint32_t c) {
+    uint64_t nb = flic_blocks_per_image(w, h);
+    uint64_t blk = kBlkHdrWords + (uint64_t)kBH * ((kBW * c * kL + 31) / 32);
+    return 4ull * (kHdrWords + nb + 1 + nb * blk);
+}
+
+extern "C" int flic_create(int device, flic_ctx **out) {
+    if (!out) return FLIC_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return FLIC_E_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return FLIC_E_NO_DEVICE;
+    flic_ctx *ctx = new (std::nothrow) flic_ctx;
+    if (!ctx) return FLIC_E_ARG;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_err, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_err, 0, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_err, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        flic_destroy(ctx);
+        return FLIC_E_CUDA;
+    }
+    *out = ctx;
+    return FLIC_OK;
+}
+
+extern "C" void flic_destroy(flic_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_status); cudaFree(ctx->d_dirE);
+    cudaFree(ctx->d_err); cudaFree(ctx->d_pix); cudaFree(ctx->d_str); cudaFree(ctx->d_off);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->h_off) cudaFreeHost(ctx->h_off);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (auto &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto &sp : ctx->free_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    delete ctx;
+}
+
+static int ensure_workspace(flic_ctx *ctx, uint64_t blocks) {
+    if (blocks <= ctx->ws_blocks) return FLIC_OK;
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_status); cudaFree(ctx->d_dirE);
+    ctx->d_hist = ctx->d_table = nullptr; ctx->d_status = ctx->d_dirE = nullptr; ctx->ws_blocks = 0;
+    CU(cudaMalloc(&ctx->d_hist, blocks * 256 * sizeof(uint16_t)));
+    CU(cudaMalloc(&ctx->d_table, blocks * 256 * sizeof(uint16_t)));
+    CU(cudaMalloc(&ctx->d_status, (blocks + 1) * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ctx->d_dirE, (blocks + 1) * sizeof(unsigned long long)));
+    ctx->ws_blocks = blocks;
+    return FLIC_OK;
+}
+
+static int make_geo(const void *base, uint32_t n, uint32_t w, uint32_t h, uint32_t c, uint32_t flags, Geo *g) {
+    if (n == 0 || w == 0 || h == 0 || c < 1 || c > 4) return FLIC_E_ARG;
+    if ((flags & 0x0Fu) != FLIC_PRED_LEFT || (flags & ~0x1Fu)) return FLIC_E_ARG;
+    g->n = n; g->w = w; g->h = h; g->c = c; g->flags = flags;
+    g->nbx = cdiv(w, kBW); g->nby = cdiv(h, kBH); g->nb = g->nbx * g->nby;
+    g->pitch = (uint64_t)w * c;
+    g->img_stride = g->pitch * h;
+    g->aligned16 = (((uintptr_t)base | g->pitch | g->img_stride) & 15u) == 0;
+    if ((uint64_t)n * g->nb >= (1ull << 31)) return FLIC_E_ARG;
+    return FLIC_OK;
+}
+
+extern "C" int flic_stage_histograms(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t n, uint32_t w, uint32_t h,
+                                     uint32_t c, uint32_t flags, uint16_t *d_hist, void *stream) {
+    if (!ctx || !d_pixels || !d_hist) return FLIC_E_ARG;
+    Geo g;
+    int rc = make_geo(d_pixels, n, w, h, c, flags, &g);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, (cudaStream_t)stream); launch_histograms(d_pixels, g, d_hist, (cudaStream_t)stream); }
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return FLIC_OK;
+}
+
+extern "C" int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t n_blocks_total, uint16_t *d_table,
+                                 void *stream) {
+    if (!ctx || !d_hist || !d_table || n_blocks_total == 0) return FLIC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    { KernelTimer t(ctx, FLIC_K_TABLES, (cudaStream_t)stream); launch_tables(d_hist, n_blocks_total, d_table, (cudaStream_t)stream); }
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return FLIC_OK;
+}
+
+extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t n, uint32_t w, uint32_t h,
+                                        uint32_t c, uint32_t flags, uint8_t *d_streams, uint64_t capacity_bytes,
+                                        uint64_t *d_offsets, void *stream) {
+    if (!ctx || !d_pixels || !d_streams || !d_offsets || ((uintptr_t)d_streams & 15u)) return FLIC_E_ARG;
+    Geo g;
+    int rc = make_geo(d_pixels, n, w, h, c, flags, &g);
+    if (rc) return rc;
+    if (capacity_bytes < 4ull * n * (kHdrWords + (uint64_t)g.nb + 1)) return FLIC_E_CAPACITY;
+    CU(cudaSetDevice(ctx->device));
+    rc = ensure_workspace(ctx, (uint64_t)n * g.nb);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint64_t cap_words = capacity_bytes / 4;
+    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s); launch_histograms(d_pixels, g, ctx->d_hist, s); }
+    { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, (uint64_t)n * g.nb, ctx->d_table, s); }
+    CU(cudaMemsetAsync(ctx->d_status, 0, ((uint64_t)n * g.nb + 1) * sizeof(unsigned long long), s));
+    { KernelTimer t(ctx, FLIC_K_PACK, s);
+      launch_pack(d_pixels, g, ctx->d_table, (uint32_t *)d_streams, cap_words, ctx->d_status, ctx->d_dirE, ctx->d_err, s); }
+    { KernelTimer t(ctx, FLIC_K_FINALIZE, s);
+      launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s); }
+    ctx->launches += 4;
+    CU(cudaGetLastError());
+    return FLIC_OK;
+}
+
+extern "C" int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams, const uint64_t *d_offsets, uint32_t n,
+                                        uint32_t w, uint32_t h, uint32_t c, uint32_t flags, uint8_t *d_pixels,
+                                        void *stream) {
+    if (!ctx || !d_pixels || !d_streams || !d_offsets || ((uintptr_t)d_streams & 3u)) return FLIC_E_ARG;
+    Geo g;
+    int rc = make_geo(d_pixels, n, w, h, c, flags, &g);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    { KernelTimer t(ctx, FLIC_K_DECODE, (cudaStream_t)stream);
+      launch_decode((const uint32_t *)d_streams, (const unsigned long long *)d_offsets, g, d_pixels, ctx->d_err,
+                    (cudaStream_t)stream); }
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return FLIC_OK;
+}
+
+extern "C" int flic_set_kernel_timing(flic_ctx *ctx, int enable) {
+    if (!ctx) return FLIC_E_ARG;
+    ctx->timing = enable != 0;
+    return FLIC_OK;
+}
+
+extern "C" int flic_get_kernel_times(flic_ctx *ctx, double ms[FLIC_K_COUNT], uint64_t counts[FLIC_K_COUNT]) {
+    if (!ctx || !ms || !counts) return FLIC_E_ARG;
+    for (int i = 0; i < FLIC_K_COUNT; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    for (auto &sp : ctx->spans) {
+        CU(cudaEventSynchronize(sp.b));
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, sp.a, sp.b));
+        ms[sp.kernel] += t;
+        counts[sp.kernel] += 1;
+        ctx->free_spans.push_back(sp);
+    }
+    ctx->spans.clear();
+    return FLIC_OK;
+}
+
+extern "C" int flic_check(flic_ctx *ctx, void *stream) {
+    if (!ctx) return FLIC_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(uint32_t), s));
+    CU(cudaStreamSynchronize(s));
+    uint32_t e = *ctx->h_err;
+    if (!e) return FLIC_OK;
+    snprintf(ctx->msg, sizeof ctx->msg, "device error bits 0x%x%s%s%s", e, (e & kErrCapacity) ? " capacity" : "",
+             (e & kErrWatchdog) ? " look-back-watchdog" : "", (e & kErrFormat) ? " format" : "");
+    if (e & kErrFormat) return FLIC_E_FORMAT;
+    if (e & kErrCapacity) return FLIC_E_CAPACITY;
+    return FLIC_E_INTERNAL;
+}
+
+// ------------------------------------------------------------ host-buffer API
+static int ensure_staging(flic_ctx *ctx, uint64_t pix, uint64_t str, uint64_t noff) {
+    if (pix > ctx->pix_cap) {
+        cudaFree(ctx->d_pix); ctx->d_pix = nullptr; ctx->pix_cap = 0;
+        CU(cudaMalloc(&ctx->d_pix, pix));
+        ctx->pix_cap = pix;
+    }
+    if (str > ctx->str_cap) {
+        cudaFree(ctx->d_str); ctx->d_str = nullptr; ctx->str_cap = 0;
+        CU(cudaMalloc(&ctx->d_str, str));
+        ctx->str_cap = str;
+    }
+    if (noff > ctx->off_cap) {
+        cudaFree(ctx->d_off); ctx->d_off = nullptr;
+        if (ctx->h_off) cudaFreeHost(ctx->h_off);
+        ctx->h_off = nullptr; ctx->off_cap = 0;
+        CU(cudaMalloc(&ctx->d_off, noff * sizeof(unsigned long long)));
+        CU(cudaMallocHost(&ctx->h_off, noff * sizeof(unsigned long long)));
+        ctx->off_cap = noff;
+    }
+    return FLIC_OK;
+}
+
+extern "C" int flic_encode_batch(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n, uint32_t w, uint32_t h, uint32_t c,
+                                 uint32_t flags, uint8_t *h_streams, uint64_t capacity_bytes, uint64_t *h_offsets) {
+    if (!ctx || !h_pixels || !h_streams || !h_offsets) return FLIC_E_ARG;
+    if (n == 0 || w == 0 || h == 0 || c < 1 || c > 4) return FLIC_E_ARG;
+    const uint64_t pix_bytes = (uint64_t)n * w * h * c;
+    const uint64_t worst = (uint64_t)n * flic_max_stream_bytes(w, h, c);
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_staging(ctx, pix_bytes, worst, (uint64_t)n + 1);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->d_pix, h_pixels, pix_bytes, cudaMemcpyHostToDevice, s));
+    rc = flic_encode_batch_device(ctx, ctx->d_pix, n, w, h, c, flags, ctx->d_str, worst, (uint64_t *)ctx->d_off, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_off, ctx->d_off, ((uint64_t)n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    rc = flic_check(ctx, s);  // synchronises
+    if (rc) return rc;
+    const uint64_t total = ctx->h_off[n];
+    if (total > capacity_bytes) return FLIC_E_CAPACITY;
+    CU(cudaMemcpyAsync(h_streams, ctx->d_str, total, cudaMemcpyDeviceToHost, s));
+    memcpy(h_offsets, ctx->h_off, ((uint64_t)n + 1) * 8);
+    CU(cudaStreamSynchronize(s));
+    return FLIC_OK;
+}
+
+extern "C" int flic_peek(const uint8_t *s, uint64_t size, flic_image_info *info) {
+    if (!s || !info || size < FLIC_HEADER_BYTES) return FLIC_E_FORMAT;
+    uint32_t wd[8];
+    memcpy(wd, s, sizeof wd);
+    if (wd[0] != kMagic || (wd[1] & 0xFFFFu) != 1u || wd[7] != (uint32_t)kL) return FLIC_E_FORMAT;
+    info->channels = (wd[1] >> 16) & 0xFFu;
+    info->flags = wd[1] >> 24;
+    info->width = wd[2];
+    info->height = wd[3];
+    info->block_w = wd[4] & 0xFFFFu;
+    info->block_h = wd[4] >> 16;
+    info->n_blocks = wd[5];
+    info->payload_words = wd[6];
+    if (info->width == 0 || info->height == 0 || info->channels < 1 || info->channels > 4) return FLIC_E_FORMAT;
+    if ((info->flags & 0x0Fu) != FLIC_PRED_LEFT || (info->flags & ~0x1Fu)) return FLIC_E_FORMAT;
+    if (info->block_w == 0 || info->block_h == 0 || (info->block_h & 1)) return FLIC_E_FORMAT;
+    if ((uint64_t)cdiv(info->width, info->block_w) * cdiv(info->height, info->block_h) != info->n_blocks)
+        return FLIC_E_FORMAT;
+    if (4ull * (kHdrWords + (uint64_t)info->n_blocks + 1 + info->payload_words) > size) return FLIC_E_FORMAT;
+    return FLIC_OK;
+}
+
+extern "C" int flic_decode_batch(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h_offsets, uint32_t n,
+                                 uint8_t *h_pixels, uint64_t pixels_capacity) {
+    if (!ctx || !h_streams || !h_offsets || !h_pixels || n == 0) return FLIC_E_ARG;
+    flic_image_info first;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (h_offsets[i + 1] < h_offsets[i] || (h_offsets[i] & 3u)) return FLIC_E_FORMAT;
+        flic_image_info info;
+        int rc = flic_peek(h_streams + h_offsets[i], h_offsets[i + 1] - h_offsets[i], &info);
+        if (rc) return rc;
+        if (info.block_w != (uint32_t)kBW || info.block_h != (uint32_t)kBH) return FLIC_E_UNSUPPORTED;
+        if (i == 0) first = info;
+        else if (info.width != first.width || info.height != first.height || info.channels != first.channels ||
+                 info.flags != first.flags)
+            return FLIC_E_UNSUPPORTED;  // one launch decodes one geometry; split mixed batches by geometry
+    }
+    const uint64_t pix_bytes = (uint64_t)n * first.width * first.height * first.channels;
+    if (pix_bytes > pixels_capacity) return FLIC_E_CAPACITY;
+    const uint64_t base = h_offsets[0], total = h_offsets[n] - base;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_staging(ctx, pix_bytes, total, (uint64_t)n + 1);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    for (uint32_t i = 0; i <= n; ++i) ctx->h_off[i] = h_offsets[i] - base;
+    CU(cudaMemcpyAsync(ctx->d_str, h_streams + base, total, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_off, ctx->h_off, ((uint64_t)n + 1) * 8, cudaMemcpyHostToDevice, s));
+    rc = flic_decode_batch_device(ctx, ctx->d_str, (const uint64_t *)ctx->d_off, n, first.width, first.height,
+                                  first.channels, first.flags, ctx->d_pix, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_pixels, ctx->d_pix, pix_bytes, cudaMemcpyDeviceToHost, s));
+    return flic_check(ctx, s);
+}
+
+// ------------------------------------------------------------------- splice
+extern "C" int flic_splice_block_rows(const uint8_t *const *parts, const uint64_t *part_sizes, uint32_t k, uint8_t *out,
+                                      uint64_t out_capacity, uint64_t *out_size) {
+    if (!parts || !part_sizes || !out || !out_size || k == 0) return FLIC_E_ARG;
+    flic_image_info first, info;
+    uint64_t nb = 0, pw = 0, height = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        int rc = flic_peek(parts[i], part_sizes[i], &info);
+        if (rc) return rc;
+        if (i == 0) first = info;
+        else if (info.width != first.width || info.channels != first.channels || info.flags != first.flags ||
+                 info.block_w != first.block_w || info.block_h != first.block_h)
+            return FLIC_E_ARG;
+        if (i + 1 < k && info.height % info.block_h) return FLIC_E_ARG;  // only the last part may be ragged
+        nb += info.n_blocks; pw += info.payload_words; height += info.height;
+    }
+    if (nb >= (1ull << 32) || pw >= (1ull << 32) || height >= (1ull << 32)) return FLIC_E_ARG;
+    const uint64_t total = 4ull * (kHdrWords + nb + 1 + pw);
+    if (total > out_capacity) return FLIC_E_CAPACITY;
+    uint32_t hdr[8] = {kMagic, 1u | (first.channels << 16) | (first.flags << 24), first.width, (uint32_t)height,
+                       first.block_w | (first.block_h << 16), (uint32_t)nb, (uint32_t)pw, (uint32_t)kL};
+    memcpy(out, hdr, sizeof hdr);
+    uint8_t *dir = out + 4 * kHdrWords, *payload = dir + 4 * (nb + 1);
+    uint32_t base = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        flic_peek(parts[i], part_sizes[i], &info);
+        const uint8_t *pdir = parts[i] + 4 * kHdrWords;
+        for (uint32_t b = 0; b < info.n_blocks; ++b) {
+            uint32_t v;
+            memcpy(&v, pdir + 4ull * b, 4);
+            v += base;
+            memcpy(dir, &v, 4);
+            dir += 4;
+        }
+        memcpy(payload, pdir + 4ull * (info.n_blocks + 1), 4ull * info.payload_words);
+        payload += 4ull * info.payload_words;
+        base += info.payload_words;
+    }
+    memcpy(dir, &base, 4);
+    *out_size = total;
+    return FLIC_OK;
+}

@@ -1,0 +1,54 @@
+"""Synthetic workloads C1..C5 (BASELINE.json `configs`, SURVEY.md §8d / BASELINE.md).
+
+Generator: numpy PCG64 (`default_rng(seed)`), fixed seeds.  One deliberate
+deviation from the survey's recipe, stated here and in DESIGN.md: the survey's
+ramp `(x+y)/4` saturates at 255 beyond x+y = 1020, which would make most of a
+4K image a flat white field (trivially compressible).  The ramp here spans the
+image diagonal (0..255 corner to corner) so every pixel carries gradient plus
+N(0, sigma=4) noise — a harder, more honest input.
+"""
+import numpy as np
+
+
+def gradient_noise(w, h, c, seed, sigma=4.0, alpha="opaque"):
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    ramp = 255.0 * (x + y) / max(w + h - 2, 1)
+    img = np.empty((h, w, c), dtype=np.uint8)
+    for ch in range(c):
+        if ch == 3:
+            img[..., 3] = 255 if alpha == "opaque" else np.clip(255.0 - ramp, 0, 255).astype(np.uint8)
+            continue
+        base = ramp if ch != 1 else 255.0 - ramp  # green runs the other way
+        noise = rng.normal(0.0, sigma, size=(h, w)).astype(np.float32)
+        img[..., ch] = np.clip(base + noise, 0, 255).astype(np.uint8)
+    return img
+
+
+def uniform_noise(w, h, c, seed):
+    return np.random.default_rng(seed).integers(0, 256, size=(h, w, c), dtype=np.uint8)
+
+
+CONFIGS = {
+    # id: (n_images, w, h, c, kind, first_seed)
+    "C1": (1, 512, 512, 3, "gradient", 1),
+    "C2": (1, 3840, 2160, 4, "gradient", 2),
+    "C3": (1024, 1920, 1080, 3, "gradient", 1000),
+    "C4": (1, 16384, 16384, 4, "gradient", 4),
+    "C5": (64, 3840, 2160, 4, "uniform", 5000),
+}
+
+
+def make_batch(cfg, n=None, distinct=8):
+    """Batch for config `cfg` as uint8 [n,h,w,c].  Only `distinct` different images are
+    synthesised (seeds first_seed..); the rest of the batch cycles through them, which
+    keeps host-side generation to seconds without changing per-image statistics."""
+    n_cfg, w, h, c, kind, seed0 = CONFIGS[cfg]
+    n = n_cfg if n is None else n
+    k = min(n, distinct)
+    gen = (lambda s: gradient_noise(w, h, c, s)) if kind == "gradient" else (lambda s: uniform_noise(w, h, c, s))
+    uniq = [gen(seed0 + i) for i in range(k)]
+    out = np.empty((n, h, w, c), dtype=np.uint8)
+    for i in range(n):
+        out[i] = uniq[i % k]
+    return out

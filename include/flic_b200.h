@@ -1,0 +1,138 @@
+/*
+ * flic_b200.h — C ABI of the B200 block-codec engine (libflicb200.so).
+ *
+ * Plain C, plain pointers and sizes; no torch / CUDA types in any signature
+ * (streams travel as void* holding a cudaStream_t).  Every entry point returns
+ * 0 (FLIC_OK) or a negative FLIC_E_* code; the library never falls back to a
+ * CPU path — with no usable sm_100 device, flic_create() fails.
+ *
+ * WHAT THIS REPLACES IN THE REFERENCE: **not stated, by necessity.**  The spec
+ * (BASELINE.json north_star) places the drop-in boundary at the reference's
+ * Rust encode/decode entry points in src/image.rs / src/main.rs.  Those files
+ * are behind the licensing gate (LICENSING.md) and were not read, so this
+ * header cannot cite the signatures it would stand in for.  The boundary below
+ * is therefore *defined here*, in the shape SURVEY.md §8(b) prescribes (batch
+ * encode/decode, caller-owned buffers, size-query call, integer status codes,
+ * one CUDA stream per call, thread-compatible not thread-safe), and
+ * INTEGRATION.md shows the generic Rust `extern "C"` block that would bind it.
+ * The bitstream it produces is the provisional FLP0 format, NOT
+ * the reference's format.
+ */
+#ifndef FLIC_B200_H
+#define FLIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLIC_OK 0
+#define FLIC_E_ARG (-1)         /* null pointer, zero dimension, channels not in 1..4, bad flags */
+#define FLIC_E_CAPACITY (-2)    /* caller-owned output buffer too small */
+#define FLIC_E_FORMAT (-3)      /* stream header / directory inconsistent */
+#define FLIC_E_CUDA (-4)        /* a CUDA call failed; see flic_last_error() */
+#define FLIC_E_NO_DEVICE (-5)   /* no sm_100 device: there is no CPU fallback */
+#define FLIC_E_UNSUPPORTED (-6) /* valid FLP0 feature this build has no kernel for */
+#define FLIC_E_INTERNAL (-7)    /* device-side consistency check tripped */
+
+#define FLIC_BLOCK_W 128        /* pixels per block row   (one CTA / one decode warp per block) */
+#define FLIC_BLOCK_H 32         /* rows per block         (one decode lane per row sub-stream)  */
+#define FLIC_MAX_CODE_LEN 11
+#define FLIC_HEADER_BYTES 32
+
+#define FLIC_PRED_LEFT 1u       /* flags bits 0-3: predictor id */
+#define FLIC_FLAG_SUBGREEN 0x10u
+
+typedef struct flic_ctx flic_ctx;
+
+typedef struct flic_image_info {
+    uint32_t width, height, channels, flags;
+    uint32_t block_w, block_h, n_blocks, payload_words;
+} flic_image_info;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int flic_create(int device, flic_ctx **out);
+void flic_destroy(flic_ctx *ctx);
+const char *flic_strerror(int code);
+const char *flic_last_error(const flic_ctx *ctx); /* detail of the last FLIC_E_CUDA / _INTERNAL */
+int flic_version(void);
+
+/* ---- size queries ------------------------------------------------------ */
+uint64_t flic_blocks_per_image(uint32_t w, uint32_t h);
+/* Worst-case bytes of ONE encoded w x h x c image (header + directory + payload). */
+uint64_t flic_max_stream_bytes(uint32_t w, uint32_t h, uint32_t c);
+
+/* ---- device-resident batch API (inputs/outputs already in HBM) --------- */
+/* Encodes n images of identical geometry, tightly packed at d_pixels
+ * (n*h*w*c bytes), into n FLP0 streams laid back to back at d_streams.
+ * d_offsets receives n+1 byte offsets (u64, device memory); stream i is
+ * [d_offsets[i], d_offsets[i+1]).  capacity_bytes >= n*flic_max_stream_bytes().
+ * Asynchronous on `stream`. */
+int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t n, uint32_t w,
+                             uint32_t h, uint32_t c, uint32_t flags, uint8_t *d_streams,
+                             uint64_t capacity_bytes, uint64_t *d_offsets, void *stream);
+
+/* Decodes n streams of identical geometry (as produced above) into tightly
+ * packed pixels.  Geometry is passed by the caller (the host API reads it
+ * from the headers).  Asynchronous on `stream`; device-side format violations
+ * surface at the next flic_check(). */
+int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams, const uint64_t *d_offsets,
+                             uint32_t n, uint32_t w, uint32_t h, uint32_t c, uint32_t flags,
+                             uint8_t *d_pixels, void *stream);
+
+/* Synchronises `stream` and reports device-side error flags raised by the
+ * kernels launched through ctx since the last check (capacity overrun,
+ * corrupt directory, look-back watchdog). */
+int flic_check(flic_ctx *ctx, void *stream);
+
+/* ---- host-buffer batch API (H2D + kernels + D2H inside the call) ------- */
+int flic_encode_batch(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n, uint32_t w, uint32_t h,
+                      uint32_t c, uint32_t flags, uint8_t *h_streams, uint64_t capacity_bytes,
+                      uint64_t *h_offsets /* n+1 */);
+int flic_decode_batch(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h_offsets,
+                      uint32_t n, uint8_t *h_pixels, uint64_t pixels_capacity);
+
+/* ---- host-only helpers -------------------------------------------------- */
+int flic_peek(const uint8_t *stream, uint64_t size, flic_image_info *info);
+
+/* Splices k streams that each hold a run of whole block rows of one image
+ * (same width/channels/flags, every part but the last a multiple of
+ * FLIC_BLOCK_H rows) into the stream of the full image.  This is the
+ * "split one oversized image by block rows" path: blocks never predict across
+ * block edges, so the parts' payloads concatenate and only the directory is
+ * rebased.  Returns bytes written via *out_size. */
+int flic_splice_block_rows(const uint8_t *const *parts, const uint64_t *part_sizes, uint32_t k,
+                           uint8_t *out, uint64_t out_capacity, uint64_t *out_size);
+
+/* ---- stage-level entry points (used by the parity tests) ---------------- */
+/* Per-block residual histograms: d_hist[n_blocks_total][256] u16. */
+int flic_stage_histograms(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t n, uint32_t w,
+                          uint32_t h, uint32_t c, uint32_t flags, uint16_t *d_hist, void *stream);
+/* Per-block code tables from histograms: d_table[n_blocks_total][256] u16,
+ * entry = len << 12 | code (len 15 = sole symbol). */
+int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t n_blocks_total,
+                      uint16_t *d_table, void *stream);
+
+/* ---- measurement hooks (bench.py) --------------------------------------- */
+#define FLIC_K_HISTOGRAMS 0
+#define FLIC_K_TABLES 1
+#define FLIC_K_PACK 2
+#define FLIC_K_FINALIZE 3
+#define FLIC_K_DECODE 4
+#define FLIC_K_COUNT 5
+/* When enabled, every kernel launched through ctx is bracketed by CUDA events
+ * recorded on the launching stream.  flic_get_kernel_times() waits for the
+ * recorded events, returns summed milliseconds and launch counts per kernel
+ * since the previous call, and clears them. */
+int flic_set_kernel_timing(flic_ctx *ctx, int enable);
+int flic_get_kernel_times(flic_ctx *ctx, double ms[FLIC_K_COUNT], uint64_t counts[FLIC_K_COUNT]);
+
+/* Number of kernel launches issued through ctx since creation (bench.py's gpu_launches). */
+uint64_t flic_launch_count(const flic_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,98 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol include/flic_b200.h
+declares, and its host-only entry points (peek, splice, size queries, argument checks) behave.
+No compute call is made here — those need a GPU (test_gpu_parity.py)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "flic_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(flic_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_exports_match_header(flic):
+    lib = C.CDLL(flic.library_path())
+    names = declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/flic_b200.h but not exported"
+    from importlib import import_module
+    codec = import_module("fast-losless-image-compression-format_b200.codec")
+    assert sorted(codec.EXPORTED) == names
+
+
+def test_constants_agree_with_header(flic):
+    text = open(os.path.join(ROOT, "include", "flic_b200.h")).read()
+    d = dict(re.findall(r"#define (FLIC_[A-Z_]+) (\(?-?\w+\)?)", text))
+    assert int(d["FLIC_BLOCK_W"]) == flic.BLOCK_W and int(d["FLIC_BLOCK_H"]) == flic.BLOCK_H
+    assert int(d["FLIC_MAX_CODE_LEN"]) == flic.MAX_CODE_LEN
+    oh = open(os.path.join(ROOT, "oracle", "flp0_oracle.h")).read()
+    assert f"#define FLP0_MAX_CODE_LEN {flic.MAX_CODE_LEN}" in oh
+
+
+def test_size_queries(flic, oracle):
+    lib = flic.load_library()
+    for (w, h, c) in [(1, 1, 1), (128, 32, 4), (129, 33, 3), (3840, 2160, 4), (1920, 1080, 3)]:
+        assert lib.flic_blocks_per_image(w, h) == -(-w // 128) * -(-h // 32)
+        assert flic.max_stream_bytes(w, h, c) == oracle.lib.flp0_max_stream_bytes(w, h, c, 128, 32)
+
+
+def test_no_device_fails_loudly(flic):
+    """On a box without an sm_100 GPU the engine refuses to start — there is no CPU fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(flic.FlicError) as e:
+        flic.Codec(0)
+    assert e.value.code == -5
+
+
+def test_peek_and_errors(flic, oracle):
+    img = cases.gradient(300, 70, 3, 5)
+    s = oracle.encode(img, 0x11)
+    info = flic.peek(s)
+    assert (info["width"], info["height"], info["channels"], info["flags"]) == (300, 70, 3, 0x11)
+    assert info["n_blocks"] == 3 * 3 and info["block_w"] == 128 and info["block_h"] == 32
+    assert 32 + 4 * (info["n_blocks"] + 1 + info["payload_words"]) == s.size
+    for bad in (s[:16], s[:-4]):
+        with pytest.raises(flic.FlicError) as e:
+            flic.peek(bad)
+        assert e.value.code == -3
+    t = s.copy(); t[0] ^= 1
+    with pytest.raises(flic.FlicError):
+        flic.peek(t)
+    t = s.copy(); t[7] = 0x02  # predictor id 2 does not exist
+    with pytest.raises(flic.FlicError):
+        flic.peek(t)
+    assert flic.load_library().flic_strerror(-5).decode().startswith("no sm_100")
+
+
+@pytest.mark.parametrize("shape,cuts", [((100, 300, 3), [64]), ((200, 130, 4), [32, 96, 160]), ((33, 50, 1), [32]),
+                                        ((64, 256, 4), [32])])
+def test_splice_block_rows(flic, oracle, shape, cuts):
+    """Streams of whole block-row runs splice (host code in the library) into exactly the full-image stream."""
+    h, w, c = shape
+    img = cases.gradient(w, h, c, 31)
+    full = oracle.encode(img)
+    edges = [0] + cuts + [h]
+    parts = [oracle.encode(img[a:b]) for a, b in zip(edges, edges[1:])]
+    assert np.array_equal(flic.splice_block_rows(parts), full)
+    assert np.array_equal(oracle.decode(flic.splice_block_rows(parts), img.shape), img)
+
+
+def test_splice_rejects_misaligned_parts(flic, oracle):
+    img = cases.gradient(140, 100, 3, 32)
+    with pytest.raises(flic.FlicError) as e:  # first part is not a whole number of block rows
+        flic.splice_block_rows([oracle.encode(img[:40]), oracle.encode(img[40:])])
+    assert e.value.code == -1
+    with pytest.raises(flic.FlicError):       # widths differ
+        flic.splice_block_rows([oracle.encode(img[:64]), oracle.encode(img[64:, :100])])

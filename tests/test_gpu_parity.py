@@ -1,0 +1,178 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA engine, called through the C ABI,
+against the CPU model of the provisional FLP0 format — byte-exact streams, pixel-exact decodes,
+stage-by-stage (histograms, code tables), plus size-independent round-trip properties at
+BASELINE.json's full sizes.  "Parity" here is engine-vs-model; parity with the reference is
+unpinned (licensing gate, LICENSING.md)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
+@pytest.mark.parametrize("flags", [0x01, 0x11])
+def test_stage_histograms_and_tables(codec, oracle, name, build, flags):
+    img = build()
+    px = dev(img[None])
+    nb = -(-img.shape[1] // 128) * -(-img.shape[0] // 32)
+    hist = torch.zeros((nb, 256), dtype=torch.int16, device="cuda")
+    table = torch.zeros((nb, 256), dtype=torch.int16, device="cuda")
+    codec.stage_histograms(px, hist, flags)
+    codec.stage_tables(hist, table)
+    codec.check()
+    want_h = oracle.block_histograms(img, flags)
+    got_h = hist.cpu().numpy().view(np.uint16)
+    assert np.array_equal(got_h, want_h), f"first bad block {np.argwhere((got_h != want_h).any(1))[:1]}"
+    got_t = table.cpu().numpy().view(np.uint16)
+    for b in range(nb):
+        assert np.array_equal(got_t[b], oracle.table(want_h[b])), f"block {b}"
+
+
+@pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
+@pytest.mark.parametrize("flags", [0x01, 0x11])
+def test_encode_bytes_and_decode_pixels(codec, oracle, name, build, flags):
+    img = build()
+    want = oracle.encode(img, flags)
+    got = codec.encode(img, flags)
+    assert got.size == want.size, (got.size, want.size)
+    assert np.array_equal(got, want), f"first differing byte {int(np.argmax(got != want))}"
+    assert np.array_equal(codec.decode(want), img)          # GPU decodes the model's stream
+    assert np.array_equal(oracle.decode(got, img.shape), img)  # model decodes the GPU's stream
+
+
+def test_golden_vectors(codec):
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        gold = json.load(f)
+    builders = dict(cases.SMALL)
+    for key, want in gold["sha256"].items():
+        name, flags = key.rsplit("@", 1)
+        s = codec.encode(builders[name](), int(flags, 16))
+        assert s.size == want["bytes"] and hashlib.sha256(s.tobytes()).hexdigest() == want["sha256"], key
+    img = np.load(os.path.join(GOLDEN, "tiny_96x40x3.npy"))
+    stream = np.fromfile(os.path.join(GOLDEN, "tiny_96x40x3.flp0"), dtype=np.uint8)
+    assert np.array_equal(codec.encode(img), stream)
+    assert np.array_equal(codec.decode(stream), img)
+
+
+def test_batch_matches_per_image(codec, oracle):
+    """A batch is the back-to-back concatenation of the per-image streams."""
+    imgs = np.stack([cases.gradient(300, 70, 3, s) for s in range(5)])
+    streams, off = codec.encode_batch(imgs)
+    assert off[0] == 0 and off[-1] == streams.size
+    for i in range(5):
+        assert np.array_equal(streams[int(off[i]): int(off[i + 1])], oracle.encode(imgs[i]))
+    assert np.array_equal(codec.decode_batch(streams, off), imgs)
+
+
+def test_unaligned_device_pointer(codec, oracle):
+    """Pixels at an address that is not 16-byte aligned take the byte-granular load/store path."""
+    img = cases.gradient(256, 64, 4, 41)
+    raw = torch.zeros(img.size + 64, dtype=torch.uint8, device="cuda")
+    px = raw[3: 3 + img.size].view(1, *img.shape)
+    px.copy_(dev(img[None]))
+    cap = codec.lib.flic_max_stream_bytes(256, 64, 4)
+    streams = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(2, dtype=torch.int64, device="cuda")
+    codec.encode_batch_device(px, streams, off)
+    codec.check()
+    n = int(off[1])
+    assert np.array_equal(streams[:n].cpu().numpy(), oracle.encode(img))
+    out_raw = torch.zeros(img.size + 64, dtype=torch.uint8, device="cuda")
+    out = out_raw[5: 5 + img.size].view(1, *img.shape)
+    codec.decode_batch_device(streams, off, out)
+    codec.check()
+    assert np.array_equal(out.cpu().numpy()[0], img)
+
+
+def test_errors_through_the_abi(codec, oracle):
+    import flic_b200 as flic
+    img = cases.gradient(256, 64, 3, 42)
+    with pytest.raises(flic.FlicError) as e:
+        codec.encode(img, flags=0x02)
+    assert e.value.code == -1
+    with pytest.raises(flic.FlicError) as e:
+        codec.encode_batch(img[None], out=np.empty(64, np.uint8))
+    assert e.value.code == -2
+    s = oracle.encode(img)
+    bad = s.copy(); bad[32 + 4] = 0xFF; bad[32 + 7] = 0x7F  # directory entry beyond the payload
+    with pytest.raises(flic.FlicError) as e:
+        codec.decode(bad)
+    assert e.value.code == -3
+    # device capacity overrun is caught by the kernels, not by an out-of-bounds write
+    px = dev(cases.noise(256, 64, 4, 1)[None])
+    small = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(2, dtype=torch.int64, device="cuda")
+    codec.encode_batch_device(px, small, off)
+    with pytest.raises(flic.FlicError) as e:
+        codec.check()
+    assert e.value.code == -2
+    assert np.array_equal(codec.decode(codec.encode(img)), img)  # context still healthy
+
+
+def test_splice_of_gpu_parts(codec):
+    """Block-row split: GPU-encoded halves splice into the GPU-encoded whole (the C4 multi-GPU path)."""
+    import flic_b200 as flic
+    img = cases.gradient(700, 200, 4, 43)
+    whole = codec.encode(img)
+    parts = [codec.encode(img[:96]), codec.encode(img[96:160]), codec.encode(img[160:])]
+    assert np.array_equal(flic.splice_block_rows(parts), whole)
+
+
+# ---- full-size, size-independent properties (BASELINE.json configs) ----
+def _roundtrip_device(codec, imgs, flags=0x01):
+    n, h, w, c = imgs.shape
+    px = dev(imgs)
+    cap = n * int(codec.lib.flic_max_stream_bytes(w, h, c))
+    streams = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    out = torch.zeros_like(px)
+    codec.encode_batch_device(px, streams, off, flags)
+    codec.decode_batch_device(streams, off, out, flags)
+    codec.check()
+    assert torch.equal(out, px)
+    return streams, off.cpu().numpy()
+
+
+def test_c2_4k_rgba_roundtrip_and_model(codec, oracle):
+    import flic_b200 as flic
+    img = flic.workloads.make_batch("C2")
+    streams, off = _roundtrip_device(codec, img)
+    got = streams[: int(off[1])].cpu().numpy()
+    assert np.array_equal(got, oracle.encode(img[0]))  # 33 MB through the scalar model: ~0.3 s
+
+
+def test_c3_batch_slice_roundtrip(codec):
+    import flic_b200 as flic
+    imgs = flic.workloads.make_batch("C3", n=48)
+    streams, off = _roundtrip_device(codec, imgs)
+    # images repeat with period 8 -> so must their streams (a checksum-of-checksums style property)
+    s = streams.cpu().numpy()
+    for i in range(8, 48):
+        assert np.array_equal(s[int(off[i]): int(off[i + 1])], s[int(off[i - 8]): int(off[i - 7])])
+
+
+def test_c5_uniform_noise_roundtrip(codec):
+    import flic_b200 as flic
+    imgs = flic.workloads.make_batch("C5", n=4)
+    _, off = _roundtrip_device(codec, imgs)
+    ratio = float(off[-1]) / imgs.size
+    assert 1.0 < ratio < 1.03  # incompressible input: 8-bit codes + 1.6 % block headers
+
+
+def test_c4_strip_roundtrip(codec):
+    """A 16384-wide, 2048-row strip of C4 (the full 1 GiB image is exercised by bench.py --workload C4)."""
+    import flic_b200 as flic
+    img = flic.workloads.gradient_noise(16384, 2048, 4, 4)[None]
+    _roundtrip_device(codec, img)

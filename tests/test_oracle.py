@@ -1,0 +1,110 @@
+"""CPU tests of the FLP0 model (oracle/).  These pin the provisional format against committed
+self-goldens; they do NOT pin anything against the reference (licensing gate — LICENSING.md)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
+@pytest.mark.parametrize("flags", [0x01, 0x11])
+def test_roundtrip(oracle, name, build, flags):
+    img = build()
+    s = oracle.encode(img, flags)
+    assert np.array_equal(oracle.decode(s, img.shape), img)
+
+
+def test_golden_streams(oracle):
+    """Committed FLP0 vectors (tests/golden/make_golden.py made them from this same model)."""
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        gold = json.load(f)
+    builders = dict(cases.SMALL)
+    for key, want in gold["sha256"].items():
+        name, flags = key.rsplit("@", 1)
+        s = oracle.encode(builders[name](), int(flags, 16))
+        assert len(s) == want["bytes"], key
+        assert hashlib.sha256(s.tobytes()).hexdigest() == want["sha256"], key
+    img = np.load(os.path.join(GOLDEN, "tiny_96x40x3.npy"))
+    stream = np.fromfile(os.path.join(GOLDEN, "tiny_96x40x3.flp0"), dtype=np.uint8)
+    assert np.array_equal(oracle.encode(img, 0x01), stream)
+    assert np.array_equal(oracle.decode(stream, img.shape), img)
+
+
+def test_known_answer_lengths(oracle):
+    """Hand-checkable Huffman cases for the length builder."""
+    h = np.zeros(256, dtype=np.uint32)
+    assert oracle.lengths(h).sum() == 0                      # empty
+    h[42] = 9
+    ln = oracle.lengths(h)
+    assert ln[42] == 15 and ln.sum() == 15                   # sole symbol: zero-length marker
+    h[:] = 0
+    h[[1, 2]] = [5, 3]
+    assert list(oracle.lengths(h)[[1, 2]]) == [1, 1]
+    h[:] = 0
+    h[[10, 20, 30, 40]] = [8, 4, 2, 1]                       # 1,2,3,3
+    assert list(oracle.lengths(h)[[10, 20, 30, 40]]) == [1, 2, 3, 3]
+    h[:] = 1                                                 # uniform 256 -> all 8
+    assert set(oracle.lengths(h)) == {8}
+
+
+def test_length_limit_and_kraft(oracle):
+    """Fibonacci counts force depth > 11; the repair must keep Kraft equality and the cap."""
+    fib = [1, 1]
+    while len(fib) < 20:
+        fib.append(fib[-1] + fib[-2])
+    h = np.zeros(256, dtype=np.uint32)
+    h[:20] = fib
+    ln = oracle.lengths(h).astype(int)
+    used = ln[ln > 0]
+    assert used.max() == 11
+    assert sum(2 ** (11 - l) for l in used) == 2 ** 11
+    # rarer symbols never get shorter codes than more frequent ones
+    order = np.argsort(h[:20], kind="stable")
+    assert all(ln[order[i]] >= ln[order[i + 1]] for i in range(19))
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        h = (rng.geometric(rng.uniform(0.01, 0.9), 256) * (rng.random(256) < rng.uniform(0.05, 1))).astype(np.uint32)
+        ln = oracle.lengths(h).astype(int)
+        used = ln[(ln > 0) & (ln != 15)]
+        if used.size:
+            assert used.max() <= 11 and sum(2 ** (11 - l) for l in used) == 2 ** 11
+
+
+def test_canonical_codes_prefix_free(oracle):
+    rng = np.random.default_rng(1)
+    h = rng.integers(0, 500, 256).astype(np.uint32)
+    t = oracle.table(h).astype(int)
+    codes = sorted((format(e & 0xFFF, "b").zfill(e >> 12) for e in t if 1 <= (e >> 12) <= 11))
+    assert all(not b.startswith(a) for a, b in zip(codes, codes[1:]))
+
+
+def test_errors(oracle):
+    img = cases.gradient(64, 64, 3, 1)
+    assert oracle.encode_rc(img, flags=0x02) == -1           # unknown predictor
+    assert oracle.encode_rc(img, flags=0x21) == -1           # reserved flag bit
+    assert oracle.encode_rc(img, cap=100) == -2              # capacity
+    s = oracle.encode(img)
+    assert oracle.decode_rc(s[:20], img.shape) == -3         # truncated header
+    assert oracle.decode_rc(s[:-8], img.shape) == -3         # truncated payload
+    bad = s.copy(); bad[0] ^= 0xFF
+    assert oracle.decode_rc(bad, img.shape) == -3            # magic
+    bad = s.copy(); bad[32 + 4] = 0xFF; bad[32 + 7] = 0x7F   # directory entry beyond payload
+    assert oracle.decode_rc(bad, img.shape) == -3
+    assert oracle.decode_rc(s, (64, 64, 2)) == -2            # output too small
+
+
+def test_blocks_are_independent(oracle):
+    """A block-row slice encodes to the same block payloads as inside the full image — the
+    property the multi-GPU block-row split relies on."""
+    img = cases.gradient(300, 100, 3, 21)
+    full = oracle.encode(img)
+    top, bot = oracle.encode(img[:64]), oracle.encode(img[64:])
+    nb_t = int(np.frombuffer(top[20:24], np.uint32)[0]); nb_b = int(np.frombuffer(bot[20:24], np.uint32)[0])
+    pay = lambda s, nb: s[32 + 4 * (nb + 1):]
+    assert np.array_equal(np.concatenate([pay(top, nb_t), pay(bot, nb_b)]), pay(full, nb_t + nb_b))
