@@ -33,6 +33,7 @@ GATE = ("licensing gate: reference README reserves all use, no licence file; BAS
 # workload name -> (config id, images per GPU per step)
 WORKLOADS = {
     "C2x64": ("C2", 64),  # configs[1] geometry (3840x2160 RGBA8) batched so a step exceeds L2 (2.1 GB raw)
+    "C2x8": ("C2", 8),    # same geometry, 265 MB/step: short enough to profile under ncu, still > L2
     "C1": ("C1", 1), "C2": ("C2", 1), "C3": ("C3", 128), "C4": ("C4", 1), "C5": ("C5", 64),
 }
 
@@ -177,6 +178,7 @@ def main():
         codec.encode_batch_device(px, streams, off, args.flags, st)
         codec.decode_batch_device(streams, off, out, args.flags, st)
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     codec.check(st)
@@ -195,7 +197,6 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = codec.launches
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     for a, m, b in ev:
         if flush is not None:

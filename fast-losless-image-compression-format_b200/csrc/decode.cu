@@ -7,7 +7,7 @@
 // shared-memory LUT (cooperatively for short codes, per lane for long ones),
 // exclusive-scan the row word counts into per-lane stream offsets, then every
 // lane runs a branch-light LUT decode with a 64-bit MSB-first bit buffer
-// (one refill per 3 symbols), undoes the left predictor in registers and
+// (one refill per 2 symbols), undoes the left predictor in registers and
 // emits 16-byte vector stores.  Column 0 is a byte-wise prefix sum down the
 // rows, done as a warp scan.
 //
@@ -25,7 +25,8 @@ struct BitReader {
     __device__ __forceinline__ void init(const uint32_t *ptr, uint32_t nwords) {
         p = ptr; words = nwords; wi = 0; n = 0; buf = 0;
     }
-    // afterwards n > 32, i.e. at least three 11-bit symbols are buffered
+    // afterwards n >= 32 (exactly 32 when the buffer had run dry), i.e. two 11-bit symbols are
+    // always buffered — three would need 33 bits, so the decoder refills every second symbol
     __device__ __forceinline__ void refill() {
         if (n <= 32u) {
             uint32_t w = wi < words ? __ldg(p + wi) : 0u;
@@ -162,7 +163,7 @@ __device__ __forceinline__ uint32_t decode_pixel(BitReader &br, const uint16_t *
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) {
         if (phase == 0) br.refill();
-        phase = phase == 2 ? 0 : phase + 1;
+        phase ^= 1;
         r |= br.get(lut) << (8 * ch);
     }
     return r;
