@@ -65,7 +65,7 @@ static int cuda_fail(flic_ctx *ctx, cudaError_t e, const char *what) {
 
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
-extern "C" int flic_version(void) { return 1; }
+extern "C" int flic_version(void) { return 2; }
 
 extern "C" const char *flic_strerror(int code) {
     switch (code) {
@@ -306,7 +306,7 @@ extern "C" int flic_peek(const uint8_t *s, uint64_t size, flic_image_info *info)
     if (!s || !info || size < FLIC_HEADER_BYTES) return FLIC_E_FORMAT;
     uint32_t wd[8];
     memcpy(wd, s, sizeof wd);
-    if (wd[0] != kMagic || (wd[1] & 0xFFFFu) != 1u || wd[7] != (uint32_t)kL) return FLIC_E_FORMAT;
+    if (wd[0] != kMagic || (wd[1] & 0xFFFFu) != 2u || wd[7] != (uint32_t)kL) return FLIC_E_FORMAT;
     info->channels = (wd[1] >> 16) & 0xFFu;
     info->flags = wd[1] >> 24;
     info->width = wd[2];
@@ -375,7 +375,7 @@ extern "C" int flic_splice_block_rows(const uint8_t *const *parts, const uint64_
     if (nb >= (1ull << 32) || pw >= (1ull << 32) || height >= (1ull << 32)) return FLIC_E_ARG;
     const uint64_t total = 4ull * (kHdrWords + nb + 1 + pw);
     if (total > out_capacity) return FLIC_E_CAPACITY;
-    uint32_t hdr[8] = {kMagic, 1u | (first.channels << 16) | (first.flags << 24), first.width, (uint32_t)height,
+    uint32_t hdr[8] = {kMagic, 2u | (first.channels << 16) | (first.flags << 24), first.width, (uint32_t)height,
                        first.block_w | (first.block_h << 16), (uint32_t)nb, (uint32_t)pw, (uint32_t)kL};
     memcpy(out, hdr, sizeof hdr);
     uint8_t *dir = out + 4 * kHdrWords, *payload = dir + 4 * (nb + 1);

@@ -66,8 +66,9 @@ __device__ __forceinline__ uint4 load_chunk16(const uint8_t *row, int off, int r
     if (nv <= 0) return v;
     if (aligned && nv >= 16) return ldg_nc_v4(row + off);
     uint32_t w[4] = {0, 0, 0, 0};
-    nv = min(nv, 16);
-    for (int j = 0; j < nv; ++j) w[j >> 2] |= (uint32_t)__ldg(row + off + j) << (8 * (j & 3));
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j < nv) w[j >> 2] |= (uint32_t)__ldg(row + off + j) << (8 * (j & 3));
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
@@ -107,12 +108,10 @@ __device__ __forceinline__ uint4 row_residuals(const uint8_t *pixels, const Geo 
     uint32_t up = 0;
     if (lane == 0 && r > 0) {
         const uint8_t *u = row - g.pitch;
-        uint32_t b[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (k < c) b[k] = __ldg(u + k);
-        if (sg) { b[0] = (b[0] - b[1]) & 0xFFu; b[2] = (b[2] - b[1]) & 0xFFu; }
-        up = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        uint32_t b0 = __ldg(u), b1 = c > 1 ? __ldg(u + 1) : 0u, b2 = c > 2 ? __ldg(u + 2) : 0u,
+                 b3 = c > 3 ? __ldg(u + 3) : 0u;
+        if (sg) { b0 = (b0 - b1) & 0xFFu; b2 = (b2 - b1) & 0xFFu; }
+        up = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
     }
 
     if (sg) {

@@ -18,22 +18,40 @@ namespace flic {
 
 constexpr int kDecWarps = 4;
 
+// predicated 32-bit read-only load: `old` is kept when pred is false (no branch, no access)
+__device__ __forceinline__ uint32_t ldg_if(const uint32_t *p, bool pred, uint32_t old) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
+        : "+r"(old)
+        : "l"(p), "r"((uint32_t)pred));
+    return old;
+}
+
+// MSB-first reader over one row sub-stream laid out per FLP0 §6: words k < minw sit in the
+// block's interleaved region (word k of row r at k*stride + r), the rest in the row's tail.
+// The next word is always prefetched into a register, and refill() is straight-line code.
 struct BitReader {
-    const uint32_t *p;
-    uint32_t words, wi, n;
+    const uint32_t *blk;             // block payload (warp-uniform)
+    uint32_t ib, stride, tb;         // element offsets: interleaved base, stride, tail base (pre-biased by -minw)
+    uint32_t minw, words, k, nextw;  // nextw holds word k
+    uint32_t n;
     unsigned long long buf;
-    __device__ __forceinline__ void init(const uint32_t *ptr, uint32_t nwords) {
-        p = ptr; words = nwords; wi = 0; n = 0; buf = 0;
+    __device__ __forceinline__ void init(const uint32_t *b, uint32_t ib_, uint32_t stride_, uint32_t tb_,
+                                         uint32_t minw_, uint32_t words_) {
+        blk = b; ib = ib_; stride = stride_; tb = tb_; minw = minw_; words = words_;
+        k = 0; n = 0; buf = 0;
+        nextw = ldg_if(blk + (0u < minw ? ib : tb), 0u < words, 0u);
     }
     // afterwards n >= 32 (exactly 32 when the buffer had run dry), i.e. two 11-bit symbols are
     // always buffered — three would need 33 bits, so the decoder refills every second symbol
     __device__ __forceinline__ void refill() {
-        if (n <= 32u) {
-            uint32_t w = wi < words ? __ldg(p + wi) : 0u;
-            ++wi;
-            buf |= (unsigned long long)w << (32u - n);
-            n += 32u;
-        }
+        const bool take = n <= 32u;
+        const unsigned long long add = ((unsigned long long)nextw << 32) >> (n & 63u);
+        buf |= take ? add : 0ull;
+        n += take ? 32u : 0u;
+        k += take ? 1u : 0u;
+        const uint32_t eo = k < minw ? ib + k * stride : tb + k;
+        nextw = ldg_if(blk + eo, take && k < words, nextw);
     }
     __device__ __forceinline__ uint32_t get(const uint16_t *lut) {
         uint32_t e = lut[(uint32_t)(buf >> (64 - kL))];
@@ -185,14 +203,11 @@ __device__ __forceinline__ void store_bytes(uint8_t *dst, uint32_t px) {
 template <int C> struct Unroll { static constexpr int U = (C == 4) ? 4 : (C == 2 ? 8 : 16); };
 
 template <int C>
-__device__ void decode_rows(const uint32_t *rowp, uint32_t words, const uint16_t *lut, uint8_t *dst,
-                            int bwa, bool active, bool sg, bool aligned, int lane) {
+__device__ void decode_rows(BitReader &br, const uint16_t *lut, uint8_t *dst, int bwa, bool active, bool sg,
+                            bool aligned, int lane) {
     constexpr int U = Unroll<C>::U;
     constexpr int W = U * C / 4;  // words per chunk
     constexpr uint32_t cmask = C == 4 ? 0xFFFFFFFFu : ((1u << (8 * (C & 3))) - 1u);
-    BitReader br;
-    br.init(rowp, active ? words : 0u);
-
     // column 0: residual against the pixel above == byte-wise prefix sum down the rows
     int phase = 0;
     uint32_t cur = active ? decode_pixel<C>(br, lut, phase) : 0u;
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) k_decode(const uint32_t *__res
         pw = sw[6];
         off = sw[kHdrWords + p.b];
         end = sw[kHdrWords + p.b + 1];
-        ok = sw[0] == kMagic && sw[2] == g.w && sw[3] == g.h && sw[5] == g.nb && fixed + pw <= swords &&
+        ok = sw[0] == kMagic && (sw[1] & 0xFFFFu) == 2u && sw[2] == g.w && sw[3] == g.h && sw[5] == g.nb && fixed + pw <= swords &&
              off <= end && end <= pw && end - off >= (uint32_t)kBlkHdrWords;
     }
     if (!ok) {
@@ -266,25 +281,30 @@ __global__ void __launch_bounds__(kDecWarps * 32) k_decode(const uint32_t *__res
 
     ok = build_lut(lut, __ldg(blk + lane), lane);
 
+    const bool active = lane < (int)p.bha;
     uint32_t rc = (__ldg(blk + 32 + (lane >> 1)) >> (16 * (lane & 1))) & 0xFFFFu;
     uint32_t incl = warp_incl_scan(rc, lane);
     uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    ok = ok && (uint32_t)kBlkHdrWords + total <= end - off;
+    uint32_t minw = active ? rc : 0xFFFFFFFFu;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) minw = min(minw, __shfl_xor_sync(0xFFFFFFFFu, minw, d));
+    ok = ok && (uint32_t)kBlkHdrWords + total <= end - off && !__any_sync(0xFFFFFFFFu, !active && rc != 0);
     if (!ok) {
         if (lane == 0) atomicOr(err, kErrFormat);
         return;
     }
-    const uint32_t *rowp = blk + kBlkHdrWords + (incl - rc);
+    BitReader br;
+    br.init(blk, kBlkHdrWords + lane, p.bha, kBlkHdrWords + minw * p.bha + (incl - rc) - lane * minw - minw, minw,
+            active ? rc : 0u);
     uint8_t *dst = pixels + (uint64_t)p.img * g.img_stride + (uint64_t)(p.y0 + lane) * g.pitch +
                    (uint64_t)p.x0 * g.c;
-    const bool active = lane < (int)p.bha;
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) != 0;
     const bool aligned = g.aligned16 != 0;
     switch (g.c) {
-        case 1: decode_rows<1>(rowp, rc, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
-        case 2: decode_rows<2>(rowp, rc, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
-        case 3: decode_rows<3>(rowp, rc, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
-        default: decode_rows<4>(rowp, rc, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
+        case 1: decode_rows<1>(br, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
+        case 2: decode_rows<2>(br, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
+        case 3: decode_rows<3>(br, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
+        default: decode_rows<4>(br, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
     }
 }
 

@@ -19,6 +19,11 @@
 
 namespace flic {
 
+// byte j of w, times four (a u32 table offset), in two instructions
+__device__ __forceinline__ uint32_t byte_x4(uint32_t w, int j) {
+    return j == 0 ? (w << 2) & 0x3FCu : (w >> (8 * j - 2)) & 0x3FCu;
+}
+
 // ---------------------------------------------------------------- k_histograms
 constexpr int kEncThreads = 256;
 constexpr int kEncWarps = kEncThreads / 32;
@@ -42,13 +47,18 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
         if (r < (int)p.bha) res[q] = row_residuals(pixels, g, p, r, lane, &nv[q]);  // warp-uniform branch
     }
     __syncthreads();
-    uint32_t *my = sh[warp];
+    char *my = reinterpret_cast<char *>(sh[warp]);
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
         const uint32_t w[4] = {res[q].x, res[q].y, res[q].z, res[q].w};
+        if (nv[q] == 16) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (j < nv[q]) atomicAdd(&my[(w[j >> 2] >> (8 * (j & 3))) & 0xFFu], 1u);
+            for (int j = 0; j < 16; ++j) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(w[j >> 2], j & 3)), 1u);
+        } else if (nv[q] > 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < nv[q]) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(w[j >> 2], j & 3)), 1u);
+        }
     }
     __syncthreads();
     uint32_t s = 0;
@@ -274,16 +284,40 @@ __device__ unsigned long long lookback(unsigned long long *status, uint64_t gb, 
     return excl;
 }
 
+constexpr int kStagePitch = kRowWordsMax + 1;  // odd pitch: the interleaving copy-out reads a column conflict-free
+
+// Looks up the lane's 16 symbols and merges them pairwise: pk[i] = (bits << 24) | code bits of
+// symbols 2i,2i+1 (at most 22 bits).  Returns the lane's total bit count.
+template <bool kFull>
+__device__ __forceinline__ uint32_t gather_pairs(const uint32_t (&w)[4], int nv, const uint32_t *tab, uint32_t (&pk)[8]) {
+    const char *t = reinterpret_cast<const char *>(tab);
+    uint32_t nbits = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        uint32_t e0 = *reinterpret_cast<const uint32_t *>(t + byte_x4(w[j >> 2], j & 3));
+        uint32_t e1 = *reinterpret_cast<const uint32_t *>(t + byte_x4(w[j >> 2], (j & 3) + 1));
+        if (!kFull) {
+            if (j >= nv) e0 = 0;
+            if (j + 1 >= nv) e1 = 0;
+        }
+        const uint32_t l1 = e1 >> 16, l = (e0 >> 16) + l1;
+        pk[j >> 1] = (((e0 & 0xFFFFu) << l1) | (e1 & 0xFFFFu)) | (l << 24);
+        nbits += l;
+    }
+    return nbits;
+}
+
 __global__ void __launch_bounds__(kEncThreads) k_pack(const uint8_t *__restrict__ pixels, Geo g,
                                                       const uint16_t *__restrict__ table,
                                                       uint32_t *__restrict__ streams, uint64_t capacity_words,
                                                       unsigned long long *status, unsigned long long *dirE,
                                                       uint32_t *err) {
-    __shared__ __align__(16) uint32_t stage[kBH][kRowWordsMax];
-    __shared__ uint16_t tab[256];
+    __shared__ __align__(16) uint32_t stage[kBH * kStagePitch];
+    __shared__ uint32_t tab[256];  // (len << 16) | code; len 0 for a sole symbol
     __shared__ uint8_t nib[256];
     __shared__ uint32_t rwc[kBH], rowoff[kBH];
     __shared__ unsigned long long s_gb, s_base;
+    __shared__ uint32_t s_minw;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t total_blocks = (uint64_t)g.n * g.nb;
 
@@ -291,8 +325,8 @@ __global__ void __launch_bounds__(kEncThreads) k_pack(const uint8_t *__restrict_
     if (tid == 0) s_gb = atomicAdd(status + total_blocks, 1ull);
     {
         uint4 z = make_uint4(0, 0, 0, 0);
-        uint4 *s4 = reinterpret_cast<uint4 *>(&stage[0][0]);
-        for (int i = tid; i < kBH * kRowWordsMax / 4; i += kEncThreads) s4[i] = z;
+        uint4 *s4 = reinterpret_cast<uint4 *>(stage);
+        for (int i = tid; i < kBH * kStagePitch / 4; i += kEncThreads) s4[i] = z;
     }
     __syncthreads();
     const uint64_t gb = s_gb;
@@ -301,7 +335,7 @@ __global__ void __launch_bounds__(kEncThreads) k_pack(const uint8_t *__restrict_
     {
         uint32_t e = table[gb * 256 + tid], l = e >> 12;
         nib[tid] = (uint8_t)l;
-        tab[tid] = (uint16_t)(l == kLenSole ? 0u : e);
+        tab[tid] = l == kLenSole ? 0u : ((l << 16) | (e & 0xFFFu));
     }
     uint4 res[kBH / kEncWarps];
     int nv[kBH / kEncWarps];
@@ -314,45 +348,48 @@ __global__ void __launch_bounds__(kEncThreads) k_pack(const uint8_t *__restrict_
     }
     __syncthreads();
 
-    // FLP0 §5: one warp per row; each lane concatenates its 16 codes, a warp scan of bit
-    // counts places them, and words are OR-scattered into the (zeroed) staging row.
+    // FLP0 §5: one warp per row.  Each lane merges its 16 codes pairwise, a warp scan of bit
+    // counts places them, and 32-bit words are OR-scattered into the zeroed staging row.
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
         const int r = warp + kEncWarps * q;
         const uint32_t w[4] = {res[q].x, res[q].y, res[q].z, res[q].w};
-        uint32_t e[16], nbits = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            e[j] = j < nv[q] ? (uint32_t)tab[(w[j >> 2] >> (8 * (j & 3))) & 0xFFu] : 0u;
-            nbits += e[j] >> 12;
-        }
+        uint32_t pk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nbits = 0;
+        if (nv[q] == 16) nbits = gather_pairs<true>(w, 16, tab, pk);
+        else if (nv[q] > 0) nbits = gather_pairs<false>(w, nv[q], tab, pk);
         const uint32_t incl = warp_incl_scan(nbits, lane);
-        const uint32_t o = incl - nbits;
-        uint32_t *dst = &stage[r][o >> 5];
-        unsigned long long acc = 0;
-        uint32_t na = o & 31u;
+        if (nbits) {
+            const uint32_t o = incl - nbits;
+            uint32_t *dst = &stage[r * kStagePitch + (o >> 5)];
+            unsigned long long acc = 0;
+            uint32_t na = o & 31u;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            uint32_t l = e[j] >> 12;
-            acc = (acc << l) | (e[j] & 0xFFFu);
-            na += l;
-            if (na >= 32u) {
-                na -= 32u;
-                atomicOr(dst++, (uint32_t)(acc >> na));
+            for (int i = 0; i < 8; ++i) {
+                acc = (acc << (pk[i] >> 24)) | (pk[i] & 0xFFFFFFu);
+                na += pk[i] >> 24;
+                if (na >= 32u) {
+                    na -= 32u;
+                    atomicOr(dst, (uint32_t)(acc >> na));
+                    ++dst;
+                }
             }
+            if (na) atomicOr(dst, (uint32_t)(acc << (32u - na)));
         }
-        if (na > 0u && nbits > 0u) atomicOr(dst, (uint32_t)(acc << (32u - na)));
         if (lane == 31) rwc[r] = (incl + 31u) >> 5;
     }
     __syncthreads();
 
     if (warp == 0) {
-        uint32_t wcount = rwc[lane];
-        uint32_t incl = warp_incl_scan(wcount, lane);
+        const uint32_t wcount = rwc[lane];
+        const uint32_t incl = warp_incl_scan(wcount, lane);
         rowoff[lane] = incl - wcount;
-        uint32_t size = kBlkHdrWords + __shfl_sync(0xFFFFFFFFu, incl, 31);
-        unsigned long long excl = lookback(status, gb, size, lane, err);
+        uint32_t mn = lane < (int)p.bha ? wcount : 0xFFFFFFFFu;  // FLP0 §6: interleave depth
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+        const uint32_t size = kBlkHdrWords + __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const unsigned long long excl = lookback(status, gb, size, lane, err);
         if (lane == 0) {
+            s_minw = mn;
             dirE[gb] = excl;
             if (gb == total_blocks - 1) dirE[total_blocks] = excl + size;
             unsigned long long base = (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + excl;
@@ -374,10 +411,23 @@ __global__ void __launch_bounds__(kEncThreads) k_pack(const uint8_t *__restrict_
     } else if (warp == 1 && lane < kBH / 2) {
         out[32 + lane] = rwc[2 * lane] | (rwc[2 * lane + 1] << 16);
     }
-    for (int r = warp; r < kBH; r += kEncWarps) {
-        const uint32_t cnt = rwc[r];
-        uint32_t *o = out + kBlkHdrWords + rowoff[r];
-        for (uint32_t i = lane; i < cnt; i += 32) o[i] = stage[r][i];
+    // interleaved region: word k of row r lands at k*bha + r (coalesced stores, conflict-free column reads)
+    const uint32_t minw = s_minw, bha = p.bha, inter = minw * bha;
+    out += kBlkHdrWords;
+    if (bha == (uint32_t)kBH) {
+        for (uint32_t i = tid; i < inter; i += kEncThreads) out[i] = stage[(i & 31u) * kStagePitch + (i >> 5)];
+    } else {
+        for (uint32_t i = tid; i < inter; i += kEncThreads) {
+            uint32_t k = i / bha, r = i - k * bha;
+            out[i] = stage[r * kStagePitch + k];
+        }
+    }
+    // tails, row by row
+    for (uint32_t r = warp; r < bha; r += kEncWarps) {
+        const uint32_t cnt = rwc[r] - minw;
+        uint32_t *o = out + inter + (rowoff[r] - r * minw);
+        const uint32_t *src = &stage[r * kStagePitch + minw];
+        for (uint32_t i = lane; i < cnt; i += 32) o[i] = src[i];
     }
 }
 
@@ -412,7 +462,7 @@ __global__ void __launch_bounds__(256) k_finalize(Geo g, const unsigned long lon
         } else {
             switch (k) {
                 case 0: v = kMagic; break;
-                case 1: v = 1u | (g.c << 16) | ((g.flags & 0xFFu) << 24); break;
+                case 1: v = 2u | (g.c << 16) | ((g.flags & 0xFFu) << 24); break;
                 case 2: v = g.w; break;
                 case 3: v = g.h; break;
                 case 4: v = (uint32_t)kBW | ((uint32_t)kBH << 16); break;

@@ -165,8 +165,10 @@ int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, u
     uint32_t nbx = ceil_div(w, bw), nby = ceil_div(h, bh), nb = nbx * nby;
     uint8_t *dir = out + FLP0_HEADER_BYTES;
     uint8_t *payload = dir + 4 * ((size_t)nb + 1);
+    if (bh > 32768) return FLP0_E_ARG;
     uint8_t *res = (uint8_t *)malloc((size_t)bw * bh * c);
-    if (!res) return FLP0_E_ARG;
+    uint8_t *rowbuf = (uint8_t *)malloc(4 * (size_t)bh * ceil_div(bw * c * L, 32u) + 4);
+    if (!res || !rowbuf) { free(res); free(rowbuf); return FLP0_E_ARG; }
 
     uint32_t wpos = 0; /* payload position in words */
     for (uint32_t by = 0; by < nby; ++by) {
@@ -188,9 +190,11 @@ int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, u
             uint8_t *blk = payload + 4 * (size_t)wpos;
             for (int s = 0; s < 256; s += 2) blk[s >> 1] = (uint8_t)(len[s] | (len[s + 1] << 4));
             uint8_t *rw = blk + 128;
-            bitw b = { rw + 2 * bh, 0, 0, 0 };
+            /* each row is bit-packed on its own ... */
+            static _Thread_local uint32_t rwc[32768];
+            uint32_t rowcap = ceil_div(bw * c * L, 32u), minw = 0xFFFFFFFFu, total = 0;
             for (uint32_t y = 0; y < bh; ++y) {
-                uint32_t before = b.words;
+                bitw b = { rowbuf + 4 * (size_t)y * rowcap, 0, 0, 0 };
                 if (y < bha) {
                     const uint8_t *r = res + (size_t)y * rowsym;
                     for (uint32_t i = 0; i < rowsym; ++i) {
@@ -198,12 +202,25 @@ int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, u
                         if (l != FLP0_LEN_SOLE) bw_put(&b, code[r[i]], l);
                     }
                     bw_flush(&b);
+                    if (b.words < minw) minw = b.words;
                 }
-                put_u16(rw + 2 * y, b.words - before);
+                rwc[y] = b.words;
+                total += b.words;
+                put_u16(rw + 2 * y, b.words);
             }
-            wpos += 32u + bh / 2u + b.words;
+            /* ... §FLP0.6: then the first minw words of the bha real rows are interleaved
+             * (word k of row r at k*bha + r) and the rows' tails follow in row order. */
+            uint8_t *o = rw + 2 * bh;
+            for (uint32_t k = 0; k < minw; ++k)
+                for (uint32_t y = 0; y < bha; ++y, o += 4) memcpy(o, rowbuf + 4 * ((size_t)y * rowcap + k), 4);
+            for (uint32_t y = 0; y < bha; ++y) {
+                memcpy(o, rowbuf + 4 * ((size_t)y * rowcap + minw), 4 * (size_t)(rwc[y] - minw));
+                o += 4 * (size_t)(rwc[y] - minw);
+            }
+            wpos += 32u + bh / 2u + total;
         }
     }
+    free(rowbuf);
     free(res);
     put_u32(dir + 4 * (size_t)nb, wpos);
 
@@ -275,11 +292,19 @@ int flp0_decode(const uint8_t *s, size_t size, uint8_t *pixels, size_t cap) {
             }
         }
         const uint8_t *rw = blk + 128;
-        const uint8_t *rowp = rw + 2 * bh;
+        const uint8_t *body = rw + 2 * bh;
+        uint32_t minw = 0xFFFFFFFFu, total = 0;
         for (uint32_t y = 0; y < bh; ++y) {
             uint32_t words = get_u16(rw + 2 * y);
-            if ((size_t)(rowp - blk) + 4 * (size_t)words > 4 * (size_t)(end - off)) { free(lut); return FLP0_E_FORMAT; }
-            if (y < bha) {
+            if (y >= bha && words) { free(lut); return FLP0_E_FORMAT; }
+            if (y < bha && words < minw) minw = words;
+            total += words;
+        }
+        if (32u + bh / 2u + total > end - off) { free(lut); return FLP0_E_FORMAT; }
+        const uint8_t *tail = body + 4 * (size_t)minw * bha;
+        for (uint32_t y = 0; y < bha; ++y) {
+            uint32_t words = get_u16(rw + 2 * y);
+            {
                 uint8_t *dst = pixels + ((size_t)(y0 + y) * w + x0) * c;
                 const uint8_t *up = dst - (size_t)w * c;
                 uint64_t acc = 0; int nacc = 0; uint32_t used = 0;
@@ -291,7 +316,9 @@ int flp0_decode(const uint8_t *s, size_t size, uint8_t *pixels, size_t cap) {
                         if (sole >= 0) r = (uint8_t)sole;
                         else {
                             if (nacc < L) {
-                                uint32_t wv = used < words ? get_u32(rowp + 4 * (size_t)used) : 0;
+                                uint32_t wv = 0;
+                                if (used < minw) wv = get_u32(body + 4 * ((size_t)used * bha + y));
+                                else if (used < words) wv = get_u32(tail + 4 * (size_t)(used - minw));
                                 used++;
                                 acc = (acc << 32) | wv; nacc += 32;
                             }
@@ -312,8 +339,8 @@ int flp0_decode(const uint8_t *s, size_t size, uint8_t *pixels, size_t cap) {
                     if ((flags & FLP0_FLAG_SUBGREEN) && c >= 3) { t[0] = (uint8_t)(t[0] + t[1]); t[2] = (uint8_t)(t[2] + t[1]); }
                     for (uint32_t ch = 0; ch < c; ++ch) dst[x * c + ch] = t[ch];
                 }
-            } else if (words) { free(lut); return FLP0_E_FORMAT; }
-            rowp += 4 * (size_t)words;
+            }
+            tail += 4 * (size_t)(words - minw);
         }
     }
     free(lut);
