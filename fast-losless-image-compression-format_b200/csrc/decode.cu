@@ -250,7 +250,7 @@ __device__ void decode_rows(BitReader &br, const uint16_t *lut, uint8_t *dst, in
     }
 }
 
-__global__ void __launch_bounds__(kDecWarps * 32) k_decode(const uint32_t *__restrict__ streams,
+__global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *__restrict__ streams,
                                                           const unsigned long long *__restrict__ offsets, Geo g,
                                                           uint8_t *__restrict__ pixels, uint32_t *err) {
     __shared__ __align__(16) uint16_t luts[kDecWarps][kLutSize];

@@ -73,24 +73,29 @@ void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, 
 }
 
 // -------------------------------------------------------------------- k_tables
-constexpr int kTabWarps = 8;
-
-struct TableScratch {
-    uint32_t key[256];  // (count << 8) | symbol, sorted ascending; unused symbols = 0xFFFFFFFF
-    uint32_t iw[256];   // internal-node weights in creation order
-    uint8_t lpar[256];  // parent (internal index) of sorted leaf i
-    uint8_t ipar[256];  // parent of internal node k
-    uint8_t idep[256];  // depth of internal node k (root = 0)
-    uint8_t len[256];   // code length per SYMBOL
-    uint32_t num[16];   // leaves per length
-    uint32_t cum[16];   // ranks < cum[l] get a length >= l
-    uint32_t next[16];  // first canonical code of each length
+// One warp owns up to 32 blocks.  Sorting and code assignment are warp-cooperative, one block at
+// a time; the inherently serial Huffman merge runs with ONE BLOCK PER LANE (all 32 lanes busy) as
+// the in-place three-pass minimum-redundancy construction of Moffat & Katajainen, whose tie rule
+// (an internal node is taken only if strictly lighter than the next leaf) is FLP0 §3.2's.
+constexpr int kTabPitch = 258;  // u16 elements per row: 129 words
+constexpr int kTabBpw = 8;      // blocks per warp: 7.7 KB of smem per warp -> ~29 warps per SM
+struct TabSmem {
+    uint32_t key[256];      // (count << 8) | symbol of the block being sorted
+    uint16_t A[kTabBpw * kTabPitch];  // merge arrays, one row per lane-owned block; odd word pitch = conflict-free in step
+    uint8_t ord[kTabBpw][256];   // sorted symbol order per block
+    uint8_t lenS[256];      // code length per SYMBOL of the block being finished
+    uint8_t lenR[256];      // code length per sorted RANK
+    uint32_t next[16];      // first canonical code per length
 };
 
 // 12 nine-bit counters (lengths 1..12) packed into two u64
-__device__ __forceinline__ void cnt_add(uint64_t &a, uint64_t &b, uint32_t l) {
-    if (l >= 1 && l <= 6) a += 1ull << (9 * (l - 1));
-    else if (l >= 7 && l <= 12) b += 1ull << (9 * (l - 7));
+__device__ __forceinline__ void cnt_add(uint64_t &a, uint64_t &b, uint32_t l, uint32_t v = 1) {
+    if (l >= 1 && l <= 6) a += (uint64_t)v << (9 * (l - 1));
+    else if (l >= 7 && l <= 12) b += (uint64_t)v << (9 * (l - 7));
+}
+__device__ __forceinline__ void cnt_sub(uint64_t &a, uint64_t &b, uint32_t l) {
+    if (l >= 1 && l <= 6) a -= 1ull << (9 * (l - 1));
+    else if (l >= 7 && l <= 12) b -= 1ull << (9 * (l - 7));
 }
 __device__ __forceinline__ uint32_t cnt_get(uint64_t a, uint64_t b, uint32_t l) {
     return (uint32_t)((l <= 6 ? a >> (9 * (l - 1)) : b >> (9 * (l - 7))) & 511u);
@@ -106,128 +111,196 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-__global__ void __launch_bounds__(kTabWarps * 32) k_tables(const uint16_t *__restrict__ hist, uint64_t nblocks,
-                                                           uint16_t *__restrict__ table) {
-    __shared__ TableScratch S[kTabWarps];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t gb = (uint64_t)blockIdx.x * kTabWarps + warp;
-    if (gb >= nblocks) return;  // whole warp leaves; no block-level sync below
-    TableScratch &s = S[warp];
-
-    // FLP0 §3.1: keys of the lane's 8 symbols
-    const uint4 hv = *reinterpret_cast<const uint4 *>(hist + gb * 256 + 8 * lane);
-    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-    uint32_t nact = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t f = (hw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu, sym = 8 * lane + k;
-        s.key[sym] = f ? ((f << 8) | sym) : 0xFFFFFFFFu;
-        s.len[sym] = 0;
-        nact += f != 0;
+// FLP0 §3.2-3.4 for one block held by one lane: sorted weights in A[i] (i < n, n >= 2)
+// -> leaves per code length (packed counters), length-limited.
+__device__ __forceinline__ void lane_lengths(uint16_t *A, int n, uint64_t &na, uint64_t &nb) {
+#define AT(i) A[(i)]
+    // pass 1: in-place merge; A[0..root) become parent pointers, A[root..next) internal weights
+    AT(0) = (uint16_t)(AT(0) + AT(1));
+    int root = 0, leaf = 2;
+    for (int next = 1; next < n - 1; ++next) {
+        uint32_t wsum;
+        if (leaf >= n || AT(root) < AT(leaf)) { wsum = AT(root); AT(root++) = (uint16_t)next; }
+        else wsum = AT(leaf++);
+        if (leaf >= n || (root < next && AT(root) < AT(leaf))) { wsum += AT(root); AT(root++) = (uint16_t)next; }
+        else wsum += AT(leaf++);
+        AT(next) = (uint16_t)wsum;
     }
-    if (lane < 16) s.num[lane] = 0;
-    const int n = (int)warp_sum(nact);
-    __syncwarp();
+    // pass 2: parent pointers -> internal depths
+    AT(n - 2) = 0;
+    for (int next = n - 3; next >= 0; --next) AT(next) = (uint16_t)(AT(AT(next)) + 1);
+    // pass 3: leaves per depth, depths beyond L folded into L
+    na = nb = 0;
+    int avbl = 1, dpth = 0;
+    root = n - 2;
+    while (avbl > 0) {
+        int used = 0;
+        while (root >= 0 && (int)AT(root) == dpth) { ++used; --root; }
+        if (avbl > used) cnt_add(na, nb, (uint32_t)min(dpth, kL), (uint32_t)(avbl - used));
+        avbl = 2 * used;
+        ++dpth;
+    }
+#undef AT
+    // Kraft repair
+    uint32_t total = 0;
+#pragma unroll
+    for (int l = 1; l <= kL; ++l) total += cnt_get(na, nb, l) << (kL - l);
+    while (total > (1u << kL)) {
+        cnt_sub(na, nb, kL);
+        for (int l = kL - 1; l >= 1; --l)
+            if (cnt_get(na, nb, l)) { cnt_sub(na, nb, l); cnt_add(na, nb, l + 1, 2); break; }
+        --total;
+    }
+}
 
-    if (n >= 2) {
-        // bitonic sort, ascending by (count, symbol)
-        for (int k = 2; k <= 256; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
+// Bitonic sort of 32*K keys held K per lane (element e = lane*K + k), ascending: strides below K
+// are register-to-register, the rest one shuffle per key.
+template <int K>
+__device__ __forceinline__ void warp_sort(uint32_t (&v)[K], int lane) {
 #pragma unroll
-                for (int t = lane; t < 128; t += 32) {
-                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), q = i | j;
-                    uint32_t a = s.key[i], b = s.key[q];
-                    bool up = (i & k) == 0;
-                    if ((a > b) == up) { s.key[i] = b; s.key[q] = a; }
+    for (int k = 2; k <= 32 * K; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= K) {
+                const int lj = j / K;
+                const bool lower = (lane & lj) == 0;
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, v[i], lj);
+                    const bool asc = (((lane * K + i) & k) == 0);
+                    v[i] = (lower == asc) ? min(v[i], o) : max(v[i], o);
                 }
-                __syncwarp();
-            }
-        }
-        // FLP0 §3.2: two-queue merge; a leaf wins a tie against an internal node
-        if (lane == 0) {
-            int li = 0, ii = 0;
-            for (int k = 0; k < n - 1; ++k) {
-                uint32_t wsum = 0;
+            } else {
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    bool leaf = li < n && (ii >= k || (s.key[li] >> 8) <= s.iw[ii]);
-                    if (leaf) { wsum += s.key[li] >> 8; s.lpar[li++] = (uint8_t)k; }
-                    else { wsum += s.iw[ii]; s.ipar[ii++] = (uint8_t)k; }
+                for (int i = 0; i < K; ++i) {
+                    if ((i & j) == 0) {
+                        const bool asc = (((lane * K + i) & k) == 0);
+                        const uint32_t a = v[i], b = v[i | j];
+                        v[i] = asc ? min(a, b) : max(a, b);
+                        v[i | j] = asc ? max(a, b) : min(a, b);
+                    }
                 }
-                s.iw[k] = wsum;
             }
-            s.idep[n - 2] = 0;
-            for (int k = n - 3; k >= 0; --k) s.idep[k] = (uint8_t)(s.idep[s.ipar[k]] + 1);
         }
-        __syncwarp();
-        // FLP0 §3.3: leaves per depth, depths beyond L folded into L
-        for (int i = lane; i < n; i += 32) {
-            uint32_t d = (uint32_t)s.idep[s.lpar[i]] + 1u;
-            atomicAdd(&s.num[min(d, (uint32_t)kL)], 1u);
-        }
-        __syncwarp();
-        // FLP0 §3.4: Kraft repair, then rank boundaries and first codes
-        if (lane == 0) {
-            uint32_t total = 0;
-            for (int l = kL; l >= 1; --l) total += s.num[l] << (kL - l);
-            while (total > (1u << kL)) {
-                s.num[kL]--;
-                for (int l = kL - 1; l >= 1; --l)
-                    if (s.num[l]) { s.num[l]--; s.num[l + 1] += 2; break; }
-                total--;
-            }
-            uint32_t c = 0;
-            for (int l = kL; l >= 1; --l) { c += s.num[l]; s.cum[l] = c; }
-            s.next[1] = 0;
-            for (int l = 2; l <= kL; ++l) s.next[l] = (s.next[l - 1] + s.num[l - 1]) << 1;
-        }
-        __syncwarp();
-        // FLP0 §3.5: lengths by sorted rank (rarest first -> longest)
-        for (int i = lane; i < n; i += 32) {
-            uint32_t l = 0;
+    }
+}
+
+// Sorts key[0..32K) in shared memory through registers and scatters (weight, symbol) of the first n.
+template <int K>
+__device__ __forceinline__ void sort_block(uint32_t *key, int n, uint16_t *Arow, uint8_t *ord, int lane) {
+    uint32_t v[K];
 #pragma unroll
-            for (int t = 1; t <= kL; ++t)
-                if ((uint32_t)i < s.cum[t]) l = t;
-            s.len[s.key[i] & 0xFFu] = (uint8_t)l;
-        }
-        __syncwarp();
-    } else if (n == 1) {
+    for (int i = 0; i < K; ++i) v[i] = key[lane * K + i];
+    warp_sort<K>(v, lane);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const int e = lane * K + i;
+        if (e < n) { Arow[e] = (uint16_t)(v[i] >> 8); ord[e] = (uint8_t)v[i]; }
+    }
+}
+
+__global__ void __launch_bounds__(32) k_tables(const uint16_t *__restrict__ hist, uint64_t nblocks,
+                                               uint16_t *__restrict__ table, int bpw) {
+    __shared__ __align__(16) TabSmem s;
+    const int lane = threadIdx.x;
+    const uint64_t first = (uint64_t)blockIdx.x * bpw;
+    const int cnt = (int)min((uint64_t)bpw, nblocks - first);
+    int myn = 0;
+
+    // ---- cooperative: compact + sort the used symbols of each block (FLP0 §3.1)
+    for (int j = 0; j < cnt; ++j) {
+        const uint4 hv = *reinterpret_cast<const uint4 *>(hist + (first + j) * 256 + 8 * lane);
+        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+        uint32_t f[8], nact = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { f[k] = (hw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu; nact += f[k] != 0; }
+        const uint32_t incl = warp_incl_scan(nact, lane);
+        const int n = (int)__shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t pos = incl - nact;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (s.key[8 * lane + k] != 0xFFFFFFFFu) s.len[8 * lane + k] = (uint8_t)kLenSole;
+            if (f[k]) s.key[pos++] = (f[k] << 8) | (uint32_t)(8 * lane + k);
+        const int P = n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256));
+        for (int i = n + lane; i < P; i += 32) s.key[i] = 0xFFFFFFFFu;
+        __syncwarp();
+        uint16_t *Arow = s.A + j * kTabPitch;
+        if (P == 32) sort_block<1>(s.key, n, Arow, s.ord[j], lane);
+        else if (P == 64) sort_block<2>(s.key, n, Arow, s.ord[j], lane);
+        else if (P == 128) sort_block<4>(s.key, n, Arow, s.ord[j], lane);
+        else sort_block<8>(s.key, n, Arow, s.ord[j], lane);
+        if (lane == j) myn = n;
         __syncwarp();
     }
 
-    // FLP0 §4: canonical codes in (length, symbol) order; the lane owns symbols 8*lane..8*lane+7
-    uint32_t l8[8];
-    uint64_t ca = 0, cb = 0;
+    // ---- one block per lane: merge, depths, census, Kraft repair (FLP0 §3.2-3.4)
+    uint64_t mya = 0, myb = 0;
+    if (lane < cnt && myn >= 2) lane_lengths(s.A + lane * kTabPitch, myn, mya, myb);
+    __syncwarp();
+
+    // ---- cooperative: lengths by rank, canonical codes, table out (FLP0 §3.5, §4)
+    for (int j = 0; j < cnt; ++j) {
+        const int n = __shfl_sync(0xFFFFFFFFu, myn, j);
+        const uint64_t na = shfl64(mya, j), nb = shfl64(myb, j);
+        reinterpret_cast<uint2 *>(s.lenS)[lane] = make_uint2(0u, 0u);
+        uint32_t nx = 0, prevnum = 0, start = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { l8[k] = s.len[8 * lane + k]; cnt_add(ca, cb, l8[k]); }
-    uint64_t ia = ca, ib = cb;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint64_t ta = shfl_up64(ia, d), tb = shfl_up64(ib, d);
-        if (lane >= d) { ia += ta; ib += tb; }
-    }
-    uint64_t ea = ia - ca, eb = ib - cb;  // symbols of each length in lower lanes
-    uint32_t out[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t l = l8[k], e = 0;
-        if (l >= 1 && l <= (uint32_t)kL) {
-            e = (l << 12) | (s.next[l] + cnt_get(ea, eb, l));
-            cnt_add(ea, eb, l);
-        } else if (l == kLenSole) {
-            e = kLenSole << 12;
+        for (int l = 1; l <= kL; ++l) {
+            nx = (nx + prevnum) << 1;
+            if (lane == 0) s.next[l] = nx;
+            prevnum = cnt_get(na, nb, l);
         }
-        out[k >> 1] |= e << (16 * (k & 1));
+#pragma unroll
+        for (int l = kL; l >= 1; --l) {  // rarest ranks first -> longest codes
+            const uint32_t c = cnt_get(na, nb, l);
+            for (uint32_t i = start + lane; i < start + c; i += 32) s.lenR[i] = (uint8_t)l;
+            start += c;
+        }
+        __syncwarp();
+        if (n >= 2) {
+            for (int i = lane; i < n; i += 32) s.lenS[s.ord[j][i]] = s.lenR[i];
+        } else if (n == 1 && lane == 0) {
+            s.lenS[s.ord[j][0]] = (uint8_t)kLenSole;
+        }
+        __syncwarp();
+        // canonical codes in (length, symbol) order; the lane owns symbols 8*lane..8*lane+7
+        const uint2 lw = reinterpret_cast<const uint2 *>(s.lenS)[lane];
+        uint32_t l8[8];
+        uint64_t ca = 0, cb = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            l8[k] = ((k < 4 ? lw.x : lw.y) >> (8 * (k & 3))) & 0xFFu;
+            cnt_add(ca, cb, l8[k]);
+        }
+        uint64_t ia = ca, ib = cb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t ta = shfl_up64(ia, d), tb = shfl_up64(ib, d);
+            if (lane >= d) { ia += ta; ib += tb; }
+        }
+        uint64_t ea = ia - ca, eb = ib - cb;  // symbols of each length in lower lanes
+        uint32_t out[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t l = l8[k], e = 0;
+            if (l >= 1 && l <= (uint32_t)kL) {
+                e = (l << 12) | (s.next[l] + cnt_get(ea, eb, l));
+                cnt_add(ea, eb, l);
+            } else if (l == kLenSole) {
+                e = kLenSole << 12;
+            }
+            out[k >> 1] |= e << (16 * (k & 1));
+        }
+        *reinterpret_cast<uint4 *>(table + (first + j) * 256 + 8 * lane) = make_uint4(out[0], out[1], out[2], out[3]);
+        __syncwarp();
     }
-    *reinterpret_cast<uint4 *>(table + gb * 256 + 8 * lane) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, cudaStream_t s) {
-    unsigned grid = (unsigned)((nblocks + kTabWarps - 1) / kTabWarps);
-    k_tables<<<grid, kTabWarps * 32, 0, s>>>(d_hist, nblocks, d_table);
+    // a few blocks per warp when that still fills the chip; kTabBpw (merge lanes busy) for large jobs
+    uint64_t want = nblocks / (148ull * 16);
+    int bpw = (int)(want < 2 ? 2 : (want > kTabBpw ? kTabBpw : want));
+    unsigned grid = (unsigned)((nblocks + bpw - 1) / bpw);
+    k_tables<<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, bpw);
 }
 
 // ---------------------------------------------------------------------- k_pack
@@ -243,77 +316,120 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
 }
 
-// Single-pass chained scan (decoupled look-back) over block payload sizes, run by warp 0.
-// Returns the exclusive prefix (words) of block gb; blocks are claimed in ticket order, so
-// every predecessor is already running and the wait is bounded.
-__device__ unsigned long long lookback(unsigned long long *status, uint64_t gb, uint32_t size, int lane,
-                                       uint32_t *err) {
-    if (lane == 0) st_status(status + gb, kFlagAgg | size);
-    unsigned long long excl = 0;
-    long long idx = (long long)gb - 1;
-    while (idx >= 0) {
-        long long my = idx - lane;
-        unsigned long long v;
-        uint32_t spins = 0;
-        bool pending;
-        do {
-            v = my >= 0 ? ld_status(status + my) : kFlagPrefix;
-            pending = __any_sync(0xFFFFFFFFu, (v >> 62) == 0);
-        } while (pending && ++spins < kSpinLimit);
-        if (pending) {
-            if (lane == 0) atomicOr(err, kErrWatchdog);
-            break;
-        }
-        uint32_t pm = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
-        unsigned long long val = v & kValMask;
-        if (pm) {
-            int first = __ffs(pm) - 1;
-            if (lane > first) val = 0;
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            uint32_t lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)val, d);
-            uint32_t hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(val >> 32), d);
-            val += ((unsigned long long)hi << 32) | lo;
-        }
-        excl += val;
-        if (pm) break;
-        idx -= 32;
+// Single-pass chained scan (decoupled look-back) over block payload sizes, run by warp 0 as a
+// resumable state machine: start() publishes this block's aggregate as soon as its size is
+// known (before any packing), poll() makes non-blocking progress between rows of packing, and
+// finish() blocks only if predecessors still have not published.  Blocks are claimed in ticket
+// order, so every predecessor is already running and the wait is bounded (watchdog otherwise).
+struct Lookback {
+    unsigned long long *status;
+    uint64_t gb;
+    long long idx;
+    unsigned long long excl;
+    uint32_t size;
+    bool done;
+
+    __device__ __forceinline__ void start(unsigned long long *st, uint64_t gb_, uint32_t size_, int lane) {
+        status = st; gb = gb_; size = size_; idx = (long long)gb_ - 1; excl = 0; done = false;
+        if (lane == 0) st_status(status + gb, kFlagAgg | size);
+        if (idx < 0) publish(lane);
     }
-    if (lane == 0) st_status(status + gb, kFlagPrefix | ((excl + size) & kValMask));
-    return excl;
-}
+    __device__ __forceinline__ void publish(int lane) {
+        done = true;
+        if (lane == 0) st_status(status + gb, kFlagPrefix | ((excl + size) & kValMask));
+    }
+    // consumes every 32-block window that is fully published; returns when one is not
+    __device__ __forceinline__ void poll(int lane) {
+        while (!done) {
+            const long long my = idx - lane;
+            const unsigned long long v = my >= 0 ? ld_status(status + my) : kFlagPrefix;
+            if (__any_sync(0xFFFFFFFFu, (v >> 62) == 0)) return;
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+            unsigned long long val = v & kValMask;
+            if (pm && lane > __ffs(pm) - 1) val = 0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                uint32_t lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)val, d);
+                uint32_t hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(val >> 32), d);
+                val += ((unsigned long long)hi << 32) | lo;
+            }
+            excl += val;
+            idx -= 32;
+            if (pm || idx < 0) publish(lane);
+        }
+    }
+    __device__ __forceinline__ void finish(int lane, uint32_t *err) {
+        uint32_t spins = 0;
+        while (!done) {
+            poll(lane);
+            if (!done && ++spins >= kSpinLimit) {
+                if (lane == 0) atomicOr(err, kErrWatchdog);
+                publish(lane);
+            }
+        }
+    }
+};
 
 constexpr int kStagePitch = kRowWordsMax + 1;  // odd pitch: the interleaving copy-out reads a column conflict-free
 
-// Looks up the lane's 16 symbols and merges them pairwise: pk[i] = (bits << 24) | code bits of
-// symbols 2i,2i+1 (at most 22 bits).  Returns the lane's total bit count.
-template <bool kFull>
-__device__ __forceinline__ uint32_t gather_pairs(const uint32_t (&w)[4], int nv, const uint32_t *tab, uint32_t (&pk)[8]) {
-    const char *t = reinterpret_cast<const char *>(tab);
-    uint32_t nbits = 0;
-#pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-        uint32_t e0 = *reinterpret_cast<const uint32_t *>(t + byte_x4(w[j >> 2], j & 3));
-        uint32_t e1 = *reinterpret_cast<const uint32_t *>(t + byte_x4(w[j >> 2], (j & 3) + 1));
-        if (!kFull) {
-            if (j >= nv) e0 = 0;
-            if (j + 1 >= nv) e1 = 0;
-        }
-        const uint32_t l1 = e1 >> 16, l = (e0 >> 16) + l1;
-        pk[j >> 1] = (((e0 & 0xFFFFu) << l1) | (e1 & 0xFFFFu)) | (l << 24);
-        nbits += l;
-    }
-    return nbits;
+// byte j of w, times eight (a uint2 table offset)
+__device__ __forceinline__ uint32_t byte_x8(uint32_t w, int j) {
+    return j == 0 ? (w << 3) & 0x7F8u : (w >> (8 * j - 3)) & 0x7F8u;
 }
 
-__global__ void __launch_bounds__(kEncThreads) k_pack(const uint8_t *__restrict__ pixels, Geo g,
+// OR `v` into shared word `saddr` iff pred — one predicated RED, no branch.
+__device__ __forceinline__ void red_or_if(uint32_t saddr, uint32_t v, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.shared.or.b32 [%0], %1;\n\t}" ::"r"(saddr),
+                 "r"(v), "r"((uint32_t)pred)
+                 : "memory");
+}
+
+// Bit count of the lane's 16 symbols (lengths only): the pre-pass that lets a block publish its
+// size before it packs a single bit.
+template <bool kFull>
+__device__ __forceinline__ uint32_t gather_bits(const uint32_t (&w)[4], int nv, const uint2 *tab) {
+    const char *t = reinterpret_cast<const char *>(tab) + 4;  // the {len << 16 | 2^len} half
+    uint32_t xs = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        uint32_t x = *reinterpret_cast<const uint32_t *>(t + byte_x8(w[j >> 2], j & 3));
+        if (!kFull && j >= nv) x = 0;
+        xs += x;  // sixteen low halves (each <= 2^11) cannot carry into the length sum
+    }
+    return xs >> 16;
+}
+
+// Looks up the lane's 16 symbols and merges them pairwise on the FMA pipe: a table entry is
+// {code, len << 16 | 2^len}, so (code0 << len1) | code1 is one IMAD.  pc[i] = code bits of
+// symbols 2i,2i+1 (at most 22), pl[i] = their bit count.  Returns the lane's total bit count.
+template <bool kFull>
+__device__ __forceinline__ uint32_t gather_pairs(const uint32_t (&w)[4], int nv, const uint2 *tab, uint32_t (&pc)[8],
+                                                 uint32_t (&pl)[8]) {
+    const char *t = reinterpret_cast<const char *>(tab);
+    uint32_t xs = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        uint2 e0 = *reinterpret_cast<const uint2 *>(t + byte_x8(w[j >> 2], j & 3));
+        uint2 e1 = *reinterpret_cast<const uint2 *>(t + byte_x8(w[j >> 2], (j & 3) + 1));
+        if (!kFull) {
+            if (j >= nv) e0 = make_uint2(0u, 1u);
+            if (j + 1 >= nv) e1 = make_uint2(0u, 1u);
+        }
+        pc[j >> 1] = e0.x * (e1.y & 0xFFFFu) + e1.x;
+        const uint32_t x = e0.y + e1.y;  // high half: len0 + len1 (the low halves cannot carry into it)
+        pl[j >> 1] = x >> 16;
+        xs += x;
+    }
+    return xs >> 16;
+}
+
+__global__ void __launch_bounds__(kEncThreads, 5) k_pack(const uint8_t *__restrict__ pixels, Geo g,
                                                       const uint16_t *__restrict__ table,
                                                       uint32_t *__restrict__ streams, uint64_t capacity_words,
                                                       unsigned long long *status, unsigned long long *dirE,
                                                       uint32_t *err) {
     __shared__ __align__(16) uint32_t stage[kBH * kStagePitch];
-    __shared__ uint32_t tab[256];  // (len << 16) | code; len 0 for a sole symbol
+    __shared__ uint2 tab[256];  // {code, len << 16 | 2^len}; len 0 for a sole symbol
     __shared__ uint8_t nib[256];
     __shared__ uint32_t rwc[kBH], rowoff[kBH];
     __shared__ unsigned long long s_gb, s_base;
@@ -335,7 +451,8 @@ __global__ void __launch_bounds__(kEncThreads) k_pack(const uint8_t *__restrict_
     {
         uint32_t e = table[gb * 256 + tid], l = e >> 12;
         nib[tid] = (uint8_t)l;
-        tab[tid] = l == kLenSole ? 0u : ((l << 16) | (e & 0xFFFu));
+        if (l == kLenSole) l = 0;
+        tab[tid] = make_uint2(l ? (e & 0xFFFu) : 0u, (l << 16) | (1u << l));
     }
     uint4 res[kBH / kEncWarps];
     int nv[kBH / kEncWarps];
@@ -348,37 +465,24 @@ __global__ void __launch_bounds__(kEncThreads) k_pack(const uint8_t *__restrict_
     }
     __syncthreads();
 
-    // FLP0 §5: one warp per row.  Each lane merges its 16 codes pairwise, a warp scan of bit
-    // counts places them, and 32-bit words are OR-scattered into the zeroed staging row.
+    // Pre-pass: bit count per lane and row -> exclusive bit offsets and exact row word counts,
+    // so the block's size is known (and published) before the expensive packing starts.
+    uint32_t off[kBH / kEncWarps];
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
         const int r = warp + kEncWarps * q;
         const uint32_t w[4] = {res[q].x, res[q].y, res[q].z, res[q].w};
-        uint32_t pk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nbits = 0;
-        if (nv[q] == 16) nbits = gather_pairs<true>(w, 16, tab, pk);
-        else if (nv[q] > 0) nbits = gather_pairs<false>(w, nv[q], tab, pk);
+        uint32_t nbits = 0;
+        if (nv[q] == 16) nbits = gather_bits<true>(w, 16, tab);
+        else if (nv[q] > 0) nbits = gather_bits<false>(w, nv[q], tab);
         const uint32_t incl = warp_incl_scan(nbits, lane);
-        if (nbits) {
-            const uint32_t o = incl - nbits;
-            uint32_t *dst = &stage[r * kStagePitch + (o >> 5)];
-            unsigned long long acc = 0;
-            uint32_t na = o & 31u;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                acc = (acc << (pk[i] >> 24)) | (pk[i] & 0xFFFFFFu);
-                na += pk[i] >> 24;
-                if (na >= 32u) {
-                    na -= 32u;
-                    atomicOr(dst, (uint32_t)(acc >> na));
-                    ++dst;
-                }
-            }
-            if (na) atomicOr(dst, (uint32_t)(acc << (32u - na)));
-        }
+        off[q] = incl - nbits;
         if (lane == 31) rwc[r] = (incl + 31u) >> 5;
     }
     __syncthreads();
 
+    Lookback lb;
+    uint32_t size = 0;
     if (warp == 0) {
         const uint32_t wcount = rwc[lane];
         const uint32_t incl = warp_incl_scan(wcount, lane);
@@ -386,10 +490,45 @@ __global__ void __launch_bounds__(kEncThreads) k_pack(const uint8_t *__restrict_
         uint32_t mn = lane < (int)p.bha ? wcount : 0xFFFFFFFFu;  // FLP0 §6: interleave depth
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
-        const uint32_t size = kBlkHdrWords + __shfl_sync(0xFFFFFFFFu, incl, 31);
-        const unsigned long long excl = lookback(status, gb, size, lane, err);
+        if (lane == 0) s_minw = mn;
+        size = kBlkHdrWords + __shfl_sync(0xFFFFFFFFu, incl, 31);
+        lb.start(status, gb, size, lane);
+    }
+
+    // FLP0 §5: one warp per row.  Each lane merges its 16 codes pairwise, places them at the bit
+    // offset found above, and ORs 32-bit words into the zeroed staging row.
+#pragma unroll
+    for (int q = 0; q < kBH / kEncWarps; ++q) {
+        const int r = warp + kEncWarps * q;
+        const uint32_t w[4] = {res[q].x, res[q].y, res[q].z, res[q].w};
+        if (warp == 0) lb.poll(lane);
+        if (nv[q] > 0) {
+            uint32_t pc[8], pl[8];
+            if (nv[q] == 16) gather_pairs<true>(w, 16, tab, pc, pl);
+            else gather_pairs<false>(w, nv[q], tab, pc, pl);
+            const uint32_t o = off[q];
+            uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[r * kStagePitch + (o >> 5)]);
+            // acc holds the pending (< 32) bits in its low end; older, already emitted bits may linger
+            // above them — every extraction below truncates to the 32 bits it wants, so they are harmless.
+            uint32_t acc = 0, na = o & 31u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const unsigned long long a64 = (unsigned long long)acc * (1u << pl[i]) + pc[i];  // IMAD.WIDE
+                na += pl[i];
+                const bool flush = na >= 32u;
+                na -= flush ? 32u : 0u;
+                red_or_if(dst, (uint32_t)(a64 >> (na & 31u)), flush);
+                dst += flush ? 4u : 0u;
+                acc = (uint32_t)a64;
+            }
+            red_or_if(dst, acc << ((32u - na) & 31u), na != 0u);
+        }
+    }
+
+    if (warp == 0) {
+        lb.finish(lane, err);
         if (lane == 0) {
-            s_minw = mn;
+            const unsigned long long excl = lb.excl;
             dirE[gb] = excl;
             if (gb == total_blocks - 1) dirE[total_blocks] = excl + size;
             unsigned long long base = (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + excl;
