@@ -18,6 +18,7 @@ struct flic_ctx {
     // per-block workspace (grown on demand)
     uint64_t ws_blocks = 0;
     uint16_t *d_hist = nullptr, *d_table = nullptr;
+    uint4 *d_resid = nullptr;  // residual plane: 16 KB per block
     unsigned long long *d_status = nullptr, *d_dirE = nullptr;
     uint32_t *d_err = nullptr;
     uint32_t *h_err = nullptr;  // pinned
@@ -121,7 +122,7 @@ extern "C" void flic_destroy(flic_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_status); cudaFree(ctx->d_dirE);
-    cudaFree(ctx->d_err); cudaFree(ctx->d_pix); cudaFree(ctx->d_str); cudaFree(ctx->d_off);
+    cudaFree(ctx->d_resid); cudaFree(ctx->d_err); cudaFree(ctx->d_pix); cudaFree(ctx->d_str); cudaFree(ctx->d_off);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->h_off) cudaFreeHost(ctx->h_off);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -133,7 +134,10 @@ extern "C" void flic_destroy(flic_ctx *ctx) {
 static int ensure_workspace(flic_ctx *ctx, uint64_t blocks) {
     if (blocks <= ctx->ws_blocks) return FLIC_OK;
     cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_status); cudaFree(ctx->d_dirE);
-    ctx->d_hist = ctx->d_table = nullptr; ctx->d_status = ctx->d_dirE = nullptr; ctx->ws_blocks = 0;
+    cudaFree(ctx->d_resid);
+    ctx->d_hist = ctx->d_table = nullptr; ctx->d_status = ctx->d_dirE = nullptr; ctx->d_resid = nullptr;
+    ctx->ws_blocks = 0;
+    CU(cudaMalloc(&ctx->d_resid, blocks * (uint64_t)kBH * 512));
     CU(cudaMalloc(&ctx->d_hist, blocks * 256 * sizeof(uint16_t)));
     CU(cudaMalloc(&ctx->d_table, blocks * 256 * sizeof(uint16_t)));
     CU(cudaMalloc(&ctx->d_status, (blocks + 1) * sizeof(unsigned long long)));
@@ -161,7 +165,7 @@ extern "C" int flic_stage_histograms(flic_ctx *ctx, const uint8_t *d_pixels, uin
     int rc = make_geo(d_pixels, n, w, h, c, flags, &g);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
-    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, (cudaStream_t)stream); launch_histograms(d_pixels, g, d_hist, (cudaStream_t)stream); }
+    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, (cudaStream_t)stream); launch_histograms(d_pixels, g, d_hist, nullptr, (cudaStream_t)stream); }
     ctx->launches += 1;
     CU(cudaGetLastError());
     return FLIC_OK;
@@ -190,11 +194,11 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const uint64_t cap_words = capacity_bytes / 4;
-    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s); launch_histograms(d_pixels, g, ctx->d_hist, s); }
+    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s); launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, s); }
     { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, (uint64_t)n * g.nb, ctx->d_table, s); }
     CU(cudaMemsetAsync(ctx->d_status, 0, ((uint64_t)n * g.nb + 1) * sizeof(unsigned long long), s));
     { KernelTimer t(ctx, FLIC_K_PACK, s);
-      launch_pack(d_pixels, g, ctx->d_table, (uint32_t *)d_streams, cap_words, ctx->d_status, ctx->d_dirE, ctx->d_err, s); }
+      launch_pack(ctx->d_resid, g, ctx->d_table, (uint32_t *)d_streams, cap_words, ctx->d_status, ctx->d_dirE, ctx->d_err, s); }
     { KernelTimer t(ctx, FLIC_K_FINALIZE, s);
       launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s); }
     ctx->launches += 4;

@@ -160,9 +160,9 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 // launchers (defined in the .cu files, used by api.cu)
-void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, cudaStream_t s);
+void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint4 *d_resid, cudaStream_t s);
 void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, cudaStream_t s);
-void launch_pack(const uint8_t *d_pixels, const Geo &g, const uint16_t *d_table, uint32_t *d_streams,
+void launch_pack(const uint4 *d_resid, const Geo &g, const uint16_t *d_table, uint32_t *d_streams,
                  uint64_t capacity_words, unsigned long long *d_status, unsigned long long *d_dirE,
                  uint32_t *d_err, cudaStream_t s);
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,

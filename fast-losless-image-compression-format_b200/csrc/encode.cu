@@ -28,8 +28,11 @@ __device__ __forceinline__ uint32_t byte_x4(uint32_t w, int j) {
 constexpr int kEncThreads = 256;
 constexpr int kEncWarps = kEncThreads / 32;
 
+// resid (optional): the "residual plane" — per block a 32 x 512-byte tile of residual bytes in
+// 16-byte lane chunks — so that k_pack does not recompute prediction (the kernels are ALU-bound,
+// HBM has headroom: one extra N-byte write buys ~20 % of k_pack's instructions).
 __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__restrict__ pixels, Geo g,
-                                                            uint16_t *__restrict__ hist) {
+                                                            uint16_t *__restrict__ hist, uint4 *__restrict__ resid) {
     __shared__ uint32_t sh[kEncWarps][256];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t gb = blockIdx.x;
@@ -45,6 +48,7 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
         nv[q] = 0;
         res[q] = make_uint4(0, 0, 0, 0);
         if (r < (int)p.bha) res[q] = row_residuals(pixels, g, p, r, lane, &nv[q]);  // warp-uniform branch
+        if (resid) resid[(gb * kBH + r) * 32 + lane] = res[q];
     }
     __syncthreads();
     char *my = reinterpret_cast<char *>(sh[warp]);
@@ -67,9 +71,9 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
     hist[gb * 256 + tid] = (uint16_t)s;
 }
 
-void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, cudaStream_t s) {
+void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint4 *d_resid, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
-    k_histograms<<<(unsigned)total, kEncThreads, 0, s>>>(d_pixels, g, d_hist);
+    k_histograms<<<(unsigned)total, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid);
 }
 
 // -------------------------------------------------------------------- k_tables
@@ -423,7 +427,7 @@ __device__ __forceinline__ uint32_t gather_pairs(const uint32_t (&w)[4], int nv,
     return xs >> 16;
 }
 
-__global__ void __launch_bounds__(kEncThreads, 5) k_pack(const uint8_t *__restrict__ pixels, Geo g,
+__global__ void __launch_bounds__(kEncThreads, 5) k_pack(const uint4 *__restrict__ resid, Geo g,
                                                       const uint16_t *__restrict__ table,
                                                       uint32_t *__restrict__ streams, uint64_t capacity_words,
                                                       unsigned long long *status, unsigned long long *dirE,
@@ -458,55 +462,25 @@ __global__ void __launch_bounds__(kEncThreads, 5) k_pack(const uint8_t *__restri
     int nv[kBH / kEncWarps];
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
-        int r = warp + kEncWarps * q;
-        nv[q] = 0;
-        res[q] = make_uint4(0, 0, 0, 0);
-        if (r < (int)p.bha) res[q] = row_residuals(pixels, g, p, r, lane, &nv[q]);
+        const int r = warp + kEncWarps * q;
+        nv[q] = r < (int)p.bha ? max(0, min(16, (int)p.rb - 16 * lane)) : 0;
+        res[q] = ldg_nc_v4(resid + (gb * kBH + r) * 32 + lane);
     }
     __syncthreads();
 
-    // Pre-pass: bit count per lane and row -> exclusive bit offsets and exact row word counts,
-    // so the block's size is known (and published) before the expensive packing starts.
-    uint32_t off[kBH / kEncWarps];
+    // FLP0 §5: one warp per row.  Each lane merges its 16 codes pairwise, a warp scan of bit counts
+    // places them, and 32-bit words are OR-ed into the zeroed staging row.
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
         const int r = warp + kEncWarps * q;
         const uint32_t w[4] = {res[q].x, res[q].y, res[q].z, res[q].w};
-        uint32_t nbits = 0;
-        if (nv[q] == 16) nbits = gather_bits<true>(w, 16, tab);
-        else if (nv[q] > 0) nbits = gather_bits<false>(w, nv[q], tab);
+        uint32_t pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nbits = 0;
+        if (nv[q] == 16) nbits = gather_pairs<true>(w, 16, tab, pc, pl);
+        else if (nv[q] > 0) nbits = gather_pairs<false>(w, nv[q], tab, pc, pl);
         const uint32_t incl = warp_incl_scan(nbits, lane);
-        off[q] = incl - nbits;
         if (lane == 31) rwc[r] = (incl + 31u) >> 5;
-    }
-    __syncthreads();
-
-    Lookback lb;
-    uint32_t size = 0;
-    if (warp == 0) {
-        const uint32_t wcount = rwc[lane];
-        const uint32_t incl = warp_incl_scan(wcount, lane);
-        rowoff[lane] = incl - wcount;
-        uint32_t mn = lane < (int)p.bha ? wcount : 0xFFFFFFFFu;  // FLP0 §6: interleave depth
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
-        if (lane == 0) s_minw = mn;
-        size = kBlkHdrWords + __shfl_sync(0xFFFFFFFFu, incl, 31);
-        lb.start(status, gb, size, lane);
-    }
-
-    // FLP0 §5: one warp per row.  Each lane merges its 16 codes pairwise, places them at the bit
-    // offset found above, and ORs 32-bit words into the zeroed staging row.
-#pragma unroll
-    for (int q = 0; q < kBH / kEncWarps; ++q) {
-        const int r = warp + kEncWarps * q;
-        const uint32_t w[4] = {res[q].x, res[q].y, res[q].z, res[q].w};
-        if (warp == 0) lb.poll(lane);
-        if (nv[q] > 0) {
-            uint32_t pc[8], pl[8];
-            if (nv[q] == 16) gather_pairs<true>(w, 16, tab, pc, pl);
-            else gather_pairs<false>(w, nv[q], tab, pc, pl);
-            const uint32_t o = off[q];
+        if (nbits) {
+            const uint32_t o = incl - nbits;
             uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[r * kStagePitch + (o >> 5)]);
             // acc holds the pending (< 32) bits in its low end; older, already emitted bits may linger
             // above them — every extraction below truncates to the 32 bits it wants, so they are harmless.
@@ -524,7 +498,21 @@ __global__ void __launch_bounds__(kEncThreads, 5) k_pack(const uint8_t *__restri
             red_or_if(dst, acc << ((32u - na) & 31u), na != 0u);
         }
     }
+    __syncthreads();
 
+    Lookback lb;
+    uint32_t size = 0;
+    if (warp == 0) {
+        const uint32_t wcount = rwc[lane];
+        const uint32_t incl = warp_incl_scan(wcount, lane);
+        rowoff[lane] = incl - wcount;
+        uint32_t mn = lane < (int)p.bha ? wcount : 0xFFFFFFFFu;  // FLP0 §6: interleave depth
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+        if (lane == 0) s_minw = mn;
+        size = kBlkHdrWords + __shfl_sync(0xFFFFFFFFu, incl, 31);
+        lb.start(status, gb, size, lane);
+    }
     if (warp == 0) {
         lb.finish(lane, err);
         if (lane == 0) {
@@ -570,11 +558,11 @@ __global__ void __launch_bounds__(kEncThreads, 5) k_pack(const uint8_t *__restri
     }
 }
 
-void launch_pack(const uint8_t *d_pixels, const Geo &g, const uint16_t *d_table, uint32_t *d_streams,
+void launch_pack(const uint4 *d_resid, const Geo &g, const uint16_t *d_table, uint32_t *d_streams,
                  uint64_t capacity_words, unsigned long long *d_status, unsigned long long *d_dirE,
                  uint32_t *d_err, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;  // caller has zeroed d_status[0..total] on this stream
-    k_pack<<<(unsigned)total, kEncThreads, 0, s>>>(d_pixels, g, d_table, d_streams, capacity_words, d_status,
+    k_pack<<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_streams, capacity_words, d_status,
                                                   d_dirE, d_err);
 }
 
