@@ -381,28 +381,6 @@ __device__ __forceinline__ uint32_t byte_x8(uint32_t w, int j) {
     return j == 0 ? (w << 3) & 0x7F8u : (w >> (8 * j - 3)) & 0x7F8u;
 }
 
-// OR `v` into shared word `saddr` iff pred — one predicated RED, no branch.
-__device__ __forceinline__ void red_or_if(uint32_t saddr, uint32_t v, bool pred) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.shared.or.b32 [%0], %1;\n\t}" ::"r"(saddr),
-                 "r"(v), "r"((uint32_t)pred)
-                 : "memory");
-}
-
-// Bit count of the lane's 16 symbols (lengths only): the pre-pass that lets a block publish its
-// size before it packs a single bit.
-template <bool kFull>
-__device__ __forceinline__ uint32_t gather_bits(const uint32_t (&w)[4], int nv, const uint2 *tab) {
-    const char *t = reinterpret_cast<const char *>(tab) + 4;  // the {len << 16 | 2^len} half
-    uint32_t xs = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        uint32_t x = *reinterpret_cast<const uint32_t *>(t + byte_x8(w[j >> 2], j & 3));
-        if (!kFull && j >= nv) x = 0;
-        xs += x;  // sixteen low halves (each <= 2^11) cannot carry into the length sum
-    }
-    return xs >> 16;
-}
-
 // Looks up the lane's 16 symbols and merges them pairwise on the FMA pipe: a table entry is
 // {code, len << 16 | 2^len}, so (code0 << len1) | code1 is one IMAD.  pc[i] = code bits of
 // symbols 2i,2i+1 (at most 22), pl[i] = their bit count.  Returns the lane's total bit count.
@@ -474,29 +452,29 @@ __global__ void __launch_bounds__(kEncThreads, 5) k_pack(const uint4 *__restrict
     for (int q = 0; q < kBH / kEncWarps; ++q) {
         const int r = warp + kEncWarps * q;
         const uint32_t w[4] = {res[q].x, res[q].y, res[q].z, res[q].w};
-        uint32_t pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nbits = 0;
+        uint32_t pc[8], pl[8], nbits;
         if (nv[q] == 16) nbits = gather_pairs<true>(w, 16, tab, pc, pl);
-        else if (nv[q] > 0) nbits = gather_pairs<false>(w, nv[q], tab, pc, pl);
+        else nbits = gather_pairs<false>(w, nv[q], tab, pc, pl);  // ragged edge / lanes past the row: zero-length entries
         const uint32_t incl = warp_incl_scan(nbits, lane);
         if (lane == 31) rwc[r] = (incl + 31u) >> 5;
-        if (nbits) {
-            const uint32_t o = incl - nbits;
-            uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[r * kStagePitch + (o >> 5)]);
-            // acc holds the pending (< 32) bits in its low end; older, already emitted bits may linger
-            // above them — every extraction below truncates to the 32 bits it wants, so they are harmless.
-            uint32_t acc = 0, na = o & 31u;
+        const uint32_t o = incl - nbits;
+        // lanes with no bits (past the row end) park on the row's first word and OR zeros into it
+        uint32_t *dst = &stage[r * kStagePitch + (nbits ? (o >> 5) : 0u)];
+        // acc holds the pending (< 32) bits in its low end; older, already emitted bits may linger above
+        // them — every extraction below truncates to the 32 bits it wants, so they are harmless.  The OR is
+        // issued unconditionally (a zero when there is nothing to flush): straight-line code, no branches.
+        uint32_t acc = 0, na = o & 31u;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const unsigned long long a64 = (unsigned long long)acc * (1u << pl[i]) + pc[i];  // IMAD.WIDE
-                na += pl[i];
-                const bool flush = na >= 32u;
-                na -= flush ? 32u : 0u;
-                red_or_if(dst, (uint32_t)(a64 >> (na & 31u)), flush);
-                dst += flush ? 4u : 0u;
-                acc = (uint32_t)a64;
-            }
-            red_or_if(dst, acc << ((32u - na) & 31u), na != 0u);
+        for (int i = 0; i < 8; ++i) {
+            const unsigned long long a64 = ((unsigned long long)acc << pl[i]) | pc[i];
+            na += pl[i];
+            const bool flush = na >= 32u;
+            na -= flush ? 32u : 0u;
+            atomicOr(dst, flush ? (uint32_t)(a64 >> (na & 31u)) : 0u);
+            dst += flush ? 1 : 0;
+            acc = (uint32_t)a64;
         }
+        atomicOr(dst, na ? acc << ((32u - na) & 31u) : 0u);
     }
     __syncthreads();
 
