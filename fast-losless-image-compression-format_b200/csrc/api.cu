@@ -3,6 +3,7 @@
 // block-row splice.  Host logic only; every byte of codec work happens in the
 // kernels of encode.cu / decode.cu.  There is no CPU fallback anywhere here.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -22,12 +23,15 @@ struct flic_ctx {
     unsigned long long *d_status = nullptr, *d_dirE = nullptr;
     uint32_t *d_err = nullptr;
     uint32_t *h_err = nullptr;  // pinned
-    // host-API staging (grown on demand)
-    uint8_t *d_pix = nullptr, *d_str = nullptr;
-    unsigned long long *d_off = nullptr;
+    // host-API pipeline: chunks of the batch flow H2D -> kernels -> D2H on three streams with
+    // double-buffered device staging, so PCIe in, compute and PCIe out overlap (grown on demand)
+    uint8_t *d_pix[2] = {nullptr, nullptr}, *d_str[2] = {nullptr, nullptr};
+    unsigned long long *d_off[2] = {nullptr, nullptr};
+    unsigned long long *h_off[2] = {nullptr, nullptr};  // pinned, off_cap entries each
     uint64_t pix_cap = 0, str_cap = 0, off_cap = 0;
-    unsigned long long *h_off = nullptr;  // pinned, off_cap entries
-    cudaStream_t stream = nullptr;        // used by the host-buffer API
+    cudaStream_t stream = nullptr;                      // kernels of the host-buffer API
+    cudaStream_t s_in = nullptr, s_out = nullptr;       // H2D / D2H
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     // opt-in per-kernel timing (flic_set_kernel_timing): event pairs recorded on the launching stream
     bool timing = false;
     struct Span { cudaEvent_t a, b; int kernel; };
@@ -110,6 +114,13 @@ extern "C" int flic_create(int device, flic_ctx **out) {
     if (e == cudaSuccess) e = cudaMemset(ctx->d_err, 0, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_err, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         flic_destroy(ctx);
         return FLIC_E_CUDA;
@@ -122,10 +133,18 @@ extern "C" void flic_destroy(flic_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_status); cudaFree(ctx->d_dirE);
-    cudaFree(ctx->d_resid); cudaFree(ctx->d_err); cudaFree(ctx->d_pix); cudaFree(ctx->d_str); cudaFree(ctx->d_off);
+    cudaFree(ctx->d_resid); cudaFree(ctx->d_err);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(ctx->d_pix[i]); cudaFree(ctx->d_str[i]); cudaFree(ctx->d_off[i]);
+        if (ctx->h_off[i]) cudaFreeHost(ctx->h_off[i]);
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
-    if (ctx->h_off) cudaFreeHost(ctx->h_off);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     for (auto &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto &sp : ctx->free_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     delete ctx;
@@ -262,48 +281,101 @@ extern "C" int flic_check(flic_ctx *ctx, void *stream) {
 // ------------------------------------------------------------ host-buffer API
 static int ensure_staging(flic_ctx *ctx, uint64_t pix, uint64_t str, uint64_t noff) {
     if (pix > ctx->pix_cap) {
-        cudaFree(ctx->d_pix); ctx->d_pix = nullptr; ctx->pix_cap = 0;
-        CU(cudaMalloc(&ctx->d_pix, pix));
+        for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_pix[i]); ctx->d_pix[i] = nullptr; }
+        ctx->pix_cap = 0;
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&ctx->d_pix[i], pix));
         ctx->pix_cap = pix;
     }
     if (str > ctx->str_cap) {
-        cudaFree(ctx->d_str); ctx->d_str = nullptr; ctx->str_cap = 0;
-        CU(cudaMalloc(&ctx->d_str, str));
+        for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_str[i]); ctx->d_str[i] = nullptr; }
+        ctx->str_cap = 0;
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&ctx->d_str[i], str + 16));
         ctx->str_cap = str;
     }
     if (noff > ctx->off_cap) {
-        cudaFree(ctx->d_off); ctx->d_off = nullptr;
-        if (ctx->h_off) cudaFreeHost(ctx->h_off);
-        ctx->h_off = nullptr; ctx->off_cap = 0;
-        CU(cudaMalloc(&ctx->d_off, noff * sizeof(unsigned long long)));
-        CU(cudaMallocHost(&ctx->h_off, noff * sizeof(unsigned long long)));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(ctx->d_off[i]); ctx->d_off[i] = nullptr;
+            if (ctx->h_off[i]) cudaFreeHost(ctx->h_off[i]);
+            ctx->h_off[i] = nullptr;
+        }
+        ctx->off_cap = 0;
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaMalloc(&ctx->d_off[i], noff * sizeof(unsigned long long)));
+            CU(cudaMallocHost(&ctx->h_off[i], noff * sizeof(unsigned long long)));
+        }
         ctx->off_cap = noff;
     }
     return FLIC_OK;
+}
+
+// images per pipeline chunk: ~256 MB of pixels, so that a 4K-RGBA batch of 64 runs as 8 chunks
+static uint32_t chunk_images(uint32_t n, uint64_t image_bytes) {
+    uint64_t target = 256ull << 20;
+    if (const char *e = getenv("FLIC_CHUNK_BYTES")) {  // test hook: force many small chunks
+        unsigned long long v = strtoull(e, nullptr, 10);
+        if (v) target = v;
+    }
+    uint64_t m = target / (image_bytes ? image_bytes : 1);
+    if (m < 1) m = 1;
+    return (uint32_t)(m > n ? n : m);
+}
+
+static int drain(flic_ctx *ctx) {  // after a failure: leave no work in flight on the staging buffers
+    cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_out);
+    return 0;
 }
 
 extern "C" int flic_encode_batch(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n, uint32_t w, uint32_t h, uint32_t c,
                                  uint32_t flags, uint8_t *h_streams, uint64_t capacity_bytes, uint64_t *h_offsets) {
     if (!ctx || !h_pixels || !h_streams || !h_offsets) return FLIC_E_ARG;
     if (n == 0 || w == 0 || h == 0 || c < 1 || c > 4) return FLIC_E_ARG;
-    const uint64_t pix_bytes = (uint64_t)n * w * h * c;
-    const uint64_t worst = (uint64_t)n * flic_max_stream_bytes(w, h, c);
+    if ((flags & 0x0Fu) != FLIC_PRED_LEFT || (flags & ~0x1Fu)) return FLIC_E_ARG;
+    const uint64_t img_bytes = (uint64_t)w * h * c, img_worst = flic_max_stream_bytes(w, h, c);
+    const uint32_t m = chunk_images(n, img_bytes);
     CU(cudaSetDevice(ctx->device));
-    int rc = ensure_staging(ctx, pix_bytes, worst, (uint64_t)n + 1);
+    int rc = ensure_staging(ctx, m * img_bytes, m * img_worst, (uint64_t)m + 1);
     if (rc) return rc;
-    cudaStream_t s = ctx->stream;
-    CU(cudaMemcpyAsync(ctx->d_pix, h_pixels, pix_bytes, cudaMemcpyHostToDevice, s));
-    rc = flic_encode_batch_device(ctx, ctx->d_pix, n, w, h, c, flags, ctx->d_str, worst, (uint64_t *)ctx->d_off, s);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->h_off, ctx->d_off, ((uint64_t)n + 1) * 8, cudaMemcpyDeviceToHost, s));
-    rc = flic_check(ctx, s);  // synchronises
-    if (rc) return rc;
-    const uint64_t total = ctx->h_off[n];
-    if (total > capacity_bytes) return FLIC_E_CAPACITY;
-    CU(cudaMemcpyAsync(h_streams, ctx->d_str, total, cudaMemcpyDeviceToHost, s));
-    memcpy(h_offsets, ctx->h_off, ((uint64_t)n + 1) * 8);
-    CU(cudaStreamSynchronize(s));
-    return FLIC_OK;
+    const uint32_t chunks = (n + m - 1) / m;
+    uint64_t out_pos = 0;
+    h_offsets[0] = 0;
+    // software pipeline: H2D(k+1) is issued before the host waits for the sizes of chunk k
+    auto issue_in = [&](uint32_t k) -> int {
+        const int b = k & 1;
+        const uint32_t first = k * m, cnt = (first + m <= n) ? m : n - first;
+        if (k >= 2) CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_k[b], 0));  // kernels of chunk k-2 have consumed d_pix[b]
+        CU(cudaMemcpyAsync(ctx->d_pix[b], h_pixels + (uint64_t)first * img_bytes, cnt * img_bytes, cudaMemcpyHostToDevice,
+                           ctx->s_in));
+        CU(cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+        return FLIC_OK;
+    };
+    rc = issue_in(0);
+    for (uint32_t k = 0; k < chunks && rc == FLIC_OK; ++k) {
+        const int b = k & 1;
+        const uint32_t first = k * m, cnt = (first + m <= n) ? m : n - first;
+        rc = [&]() -> int {
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+            if (k >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));  // D2H of chunk k-2 has drained d_str[b]
+            int r = flic_encode_batch_device(ctx, ctx->d_pix[b], cnt, w, h, c, flags, ctx->d_str[b], cnt * img_worst,
+                                             (uint64_t *)ctx->d_off[b], ctx->stream);
+            if (r) return r;
+            CU(cudaMemcpyAsync(ctx->h_off[b], ctx->d_off[b], ((uint64_t)cnt + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+            if (k + 1 < chunks) { r = issue_in(k + 1); if (r) return r; }
+            CU(cudaEventSynchronize(ctx->ev_k[b]));
+            const uint64_t total = ctx->h_off[b][cnt];
+            if (total > cnt * img_worst) return FLIC_E_INTERNAL;  // kernels flagged a capacity overrun
+            if (out_pos + total > capacity_bytes) return FLIC_E_CAPACITY;
+            for (uint32_t i = 1; i <= cnt; ++i) h_offsets[first + i] = out_pos + ctx->h_off[b][i];
+            CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[b], 0));
+            CU(cudaMemcpyAsync(h_streams + out_pos, ctx->d_str[b], total, cudaMemcpyDeviceToHost, ctx->s_out));
+            CU(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
+            out_pos += total;
+            return FLIC_OK;
+        }();
+    }
+    if (rc) { drain(ctx); flic_check(ctx, ctx->stream); return rc; }
+    CU(cudaStreamSynchronize(ctx->s_out));
+    return flic_check(ctx, ctx->stream);
 }
 
 extern "C" int flic_peek(const uint8_t *s, uint64_t size, flic_image_info *info) {
@@ -343,21 +415,42 @@ extern "C" int flic_decode_batch(flic_ctx *ctx, const uint8_t *h_streams, const 
                  info.flags != first.flags)
             return FLIC_E_UNSUPPORTED;  // one launch decodes one geometry; split mixed batches by geometry
     }
-    const uint64_t pix_bytes = (uint64_t)n * first.width * first.height * first.channels;
-    if (pix_bytes > pixels_capacity) return FLIC_E_CAPACITY;
-    const uint64_t base = h_offsets[0], total = h_offsets[n] - base;
+    const uint64_t img_bytes = (uint64_t)first.width * first.height * first.channels;
+    if ((uint64_t)n * img_bytes > pixels_capacity) return FLIC_E_CAPACITY;
+    const uint32_t m = chunk_images(n, img_bytes);
+    const uint32_t chunks = (n + m - 1) / m;
+    uint64_t max_str = 0;
+    for (uint32_t k = 0; k < chunks; ++k) {
+        const uint32_t f0 = k * m, f1 = (f0 + m <= n) ? f0 + m : n;
+        const uint64_t sz = h_offsets[f1] - h_offsets[f0];
+        if (sz > max_str) max_str = sz;
+    }
     CU(cudaSetDevice(ctx->device));
-    int rc = ensure_staging(ctx, pix_bytes, total, (uint64_t)n + 1);
+    int rc = ensure_staging(ctx, m * img_bytes, max_str, (uint64_t)m + 1);
     if (rc) return rc;
-    cudaStream_t s = ctx->stream;
-    for (uint32_t i = 0; i <= n; ++i) ctx->h_off[i] = h_offsets[i] - base;
-    CU(cudaMemcpyAsync(ctx->d_str, h_streams + base, total, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->d_off, ctx->h_off, ((uint64_t)n + 1) * 8, cudaMemcpyHostToDevice, s));
-    rc = flic_decode_batch_device(ctx, ctx->d_str, (const uint64_t *)ctx->d_off, n, first.width, first.height,
-                                  first.channels, first.flags, ctx->d_pix, s);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(h_pixels, ctx->d_pix, pix_bytes, cudaMemcpyDeviceToHost, s));
-    return flic_check(ctx, s);
+    for (uint32_t k = 0; k < chunks; ++k) {
+        const int b = k & 1;
+        const uint32_t f0 = k * m, cnt = (f0 + m <= n) ? m : n - f0;
+        const uint64_t base = h_offsets[f0], sz = h_offsets[f0 + cnt] - base;
+        // the pinned offsets and d_str[b] of chunk k-2 must have been consumed by its kernel
+        if (k >= 2) { CU(cudaEventSynchronize(ctx->ev_k[b])); }
+        for (uint32_t i = 0; i <= cnt; ++i) ctx->h_off[b][i] = h_offsets[f0 + i] - base;
+        CU(cudaMemcpyAsync(ctx->d_str[b], h_streams + base, sz, cudaMemcpyHostToDevice, ctx->s_in));
+        CU(cudaMemcpyAsync(ctx->d_off[b], ctx->h_off[b], ((uint64_t)cnt + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        CU(cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        if (k >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));  // D2H of chunk k-2 has drained d_pix[b]
+        rc = flic_decode_batch_device(ctx, ctx->d_str[b], (const uint64_t *)ctx->d_off[b], cnt, first.width, first.height,
+                                      first.channels, first.flags, ctx->d_pix[b], ctx->stream);
+        if (rc) { drain(ctx); return rc; }
+        CU(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[b], 0));
+        CU(cudaMemcpyAsync(h_pixels + (uint64_t)f0 * img_bytes, ctx->d_pix[b], cnt * img_bytes, cudaMemcpyDeviceToHost,
+                           ctx->s_out));
+        CU(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
+    }
+    CU(cudaStreamSynchronize(ctx->s_out));
+    return flic_check(ctx, ctx->stream);
 }
 
 // ------------------------------------------------------------------- splice

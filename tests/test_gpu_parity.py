@@ -76,6 +76,21 @@ def test_batch_matches_per_image(codec, oracle):
     assert np.array_equal(codec.decode_batch(streams, off), imgs)
 
 
+def test_host_pipeline_many_chunks(codec, oracle, monkeypatch):
+    """The host-buffer API streams the batch through double-buffered chunks; force 1-2 images per chunk
+    so buffer reuse (chunk k vs k-2) and the offset rebasing are exercised, odd tail chunk included."""
+    imgs = np.stack([cases.gradient(300, 70, 3, 100 + s) for s in range(11)])
+    monkeypatch.setenv("FLIC_CHUNK_BYTES", str(2 * imgs[0].nbytes))
+    streams, off = codec.encode_batch(imgs)
+    want = np.concatenate([oracle.encode(im) for im in imgs])
+    assert off[-1] == want.size and np.array_equal(streams, want)
+    assert np.array_equal(codec.decode_batch(streams, off), imgs)
+    monkeypatch.setenv("FLIC_CHUNK_BYTES", "1")  # one image per chunk
+    s1, o1 = codec.encode_batch(imgs)
+    assert np.array_equal(s1, want) and np.array_equal(o1, off)
+    assert np.array_equal(codec.decode_batch(s1, o1), imgs)
+
+
 def test_unaligned_device_pointer(codec, oracle):
     """Pixels at an address that is not 16-byte aligned take the byte-granular load/store path."""
     img = cases.gradient(256, 64, 4, 41)
