@@ -141,6 +141,44 @@ __device__ __forceinline__ uint4 row_residuals(const uint8_t *pixels, const Geo 
     return res;
 }
 
+// Fast path of row_residuals for a full-width (128-pixel) block row of a 16-byte-aligned image:
+// channels and the colour transform are compile-time, `row` already points at the lane's chunk.
+template <int C, bool SG>
+__device__ __forceinline__ uint4 row_residuals_fast(const uint8_t *row, uint64_t pitch, int r, int lane, int *nv) {
+    constexpr int kLanes = kBW * C / 16;  // lanes that own bytes of the row
+    const bool own = lane < kLanes;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (own) v = ldg_nc_v4(row);
+    *nv = own ? 16 : 0;
+    uint32_t up = 0;
+    if (lane == 0 && r > 0) {
+        up = __ldg(reinterpret_cast<const uint32_t *>(row - pitch));  // 4-byte aligned: row is 16-byte aligned
+        if (C < 4) up &= (1u << (8 * (C & 3))) - 1u;
+        if (SG && C >= 3) up = subgreen4(up);  // bytes 0,2 minus byte 1; byte 3 (alpha or masked) untouched
+    }
+    if (SG && C == 4) {
+        v.x = subgreen4(v.x); v.y = subgreen4(v.y); v.z = subgreen4(v.z); v.w = subgreen4(v.w);
+    } else if (SG && C == 3) {
+        const uint32_t pw = __shfl_up_sync(0xFFFFFFFFu, v.w, 1), nw = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
+        const int ph = lane % 3;
+        uint4 t;
+        t.x = subgreen3(pw, v.x, v.y, ph);
+        t.y = subgreen3(v.x, v.y, v.z, (ph + 1) % 3);
+        t.z = subgreen3(v.y, v.z, v.w, (ph + 2) % 3);
+        t.w = subgreen3(v.z, v.w, nw, ph);
+        v = t;
+    }
+    constexpr int sh = 8 * (4 - C);
+    uint32_t pl = __shfl_up_sync(0xFFFFFFFFu, v.w, 1);
+    if (lane == 0) pl = up << sh;
+    uint4 res;
+    res.x = __vsub4(v.x, __funnelshift_r(pl, v.x, sh));
+    res.y = __vsub4(v.y, __funnelshift_r(v.x, v.y, sh));
+    res.z = __vsub4(v.z, __funnelshift_r(v.y, v.z, sh));
+    res.w = __vsub4(v.w, __funnelshift_r(v.z, v.w, sh));
+    return res;
+}
+
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
     v += __shfl_xor_sync(0xFFFFFFFFu, v, 16);
     v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);

@@ -31,6 +31,7 @@ constexpr int kEncWarps = kEncThreads / 32;
 // resid (optional): the "residual plane" — per block a 32 x 512-byte tile of residual bytes in
 // 16-byte lane chunks — so that k_pack does not recompute prediction (the kernels are ALU-bound,
 // HBM has headroom: one extra N-byte write buys ~20 % of k_pack's instructions).
+template <int C, bool SG>
 __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__restrict__ pixels, Geo g,
                                                             uint16_t *__restrict__ hist, uint4 *__restrict__ resid) {
     __shared__ uint32_t sh[kEncWarps][256];
@@ -42,13 +43,27 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
 
     uint4 res[kBH / kEncWarps];
     int nv[kBH / kEncWarps];
+    if (g.aligned16 && p.bwa == (uint32_t)kBW) {  // block-uniform: full-width rows of an aligned image
+        const uint8_t *row = pixels + (uint64_t)p.img * g.img_stride + (uint64_t)(p.y0 + warp) * g.pitch +
+                             (uint64_t)p.x0 * C + 16 * lane;
 #pragma unroll
-    for (int q = 0; q < kBH / kEncWarps; ++q) {
-        int r = warp + kEncWarps * q;
-        nv[q] = 0;
-        res[q] = make_uint4(0, 0, 0, 0);
-        if (r < (int)p.bha) res[q] = row_residuals(pixels, g, p, r, lane, &nv[q]);  // warp-uniform branch
-        if (resid) resid[(gb * kBH + r) * 32 + lane] = res[q];
+        for (int q = 0; q < kBH / kEncWarps; ++q) {
+            const int r = warp + kEncWarps * q;
+            nv[q] = 0;
+            res[q] = make_uint4(0, 0, 0, 0);
+            if (r < (int)p.bha) res[q] = row_residuals_fast<C, SG>(row, g.pitch, r, lane, &nv[q]);  // warp-uniform
+            if (resid) resid[(gb * kBH + r) * 32 + lane] = res[q];
+            row += kEncWarps * g.pitch;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < kBH / kEncWarps; ++q) {
+            const int r = warp + kEncWarps * q;
+            nv[q] = 0;
+            res[q] = make_uint4(0, 0, 0, 0);
+            if (r < (int)p.bha) res[q] = row_residuals(pixels, g, p, r, lane, &nv[q]);
+            if (resid) resid[(gb * kBH + r) * 32 + lane] = res[q];
+        }
     }
     __syncthreads();
     char *my = reinterpret_cast<char *>(sh[warp]);
@@ -73,7 +88,16 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
 
 void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint4 *d_resid, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
-    k_histograms<<<(unsigned)total, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid);
+    const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) && g.c >= 3;
+    const unsigned grid = (unsigned)total;
+#define FLIC_HIST(C, SG) k_histograms<C, SG><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid)
+    switch (g.c) {
+        case 1: FLIC_HIST(1, false); break;
+        case 2: FLIC_HIST(2, false); break;
+        case 3: if (sg) FLIC_HIST(3, true); else FLIC_HIST(3, false); break;
+        default: if (sg) FLIC_HIST(4, true); else FLIC_HIST(4, false); break;
+    }
+#undef FLIC_HIST
 }
 
 // -------------------------------------------------------------------- k_tables
