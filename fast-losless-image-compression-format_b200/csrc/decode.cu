@@ -29,29 +29,33 @@ __device__ __forceinline__ uint32_t ldg_if(const uint32_t *p, bool pred, uint32_
 
 // MSB-first reader over one row sub-stream laid out per FLP0 §6: words k < minw sit in the
 // block's interleaved region (word k of row r at k*stride + r), the rest in the row's tail.
-// The next word is always prefetched into a register, and refill() is straight-line code.
+// Two stream words are always queued in registers (q0 = word k, q1 = word k+1): a word is
+// requested four symbols before it is used, which rides out an L1 miss; refill() is
+// straight-line code with one predicated load.
 struct BitReader {
-    const uint32_t *blk;             // block payload (warp-uniform)
-    uint32_t ib, stride, tb;         // element offsets: interleaved base, stride, tail base (pre-biased by -minw)
-    uint32_t minw, words, k, nextw;  // nextw holds word k
-    uint32_t n;
+    const uint32_t *blk;          // block payload (warp-uniform)
+    uint32_t ib, stride, tb;      // element offsets: interleaved base, stride, tail base (pre-biased by -minw)
+    uint32_t minw, words, k;      // k = index of the word held in q0
+    uint32_t q0, q1, n;
     unsigned long long buf;
+    __device__ __forceinline__ uint32_t eo(uint32_t i) const { return i < minw ? ib + i * stride : tb + i; }
     __device__ __forceinline__ void init(const uint32_t *b, uint32_t ib_, uint32_t stride_, uint32_t tb_,
                                          uint32_t minw_, uint32_t words_) {
         blk = b; ib = ib_; stride = stride_; tb = tb_; minw = minw_; words = words_;
         k = 0; n = 0; buf = 0;
-        nextw = ldg_if(blk + (0u < minw ? ib : tb), 0u < words, 0u);
+        q0 = ldg_if(blk + eo(0), 0u < words, 0u);
+        q1 = ldg_if(blk + eo(1), 1u < words, 0u);
     }
     // afterwards n >= 32 (exactly 32 when the buffer had run dry), i.e. two 11-bit symbols are
     // always buffered — three would need 33 bits, so the decoder refills every second symbol
     __device__ __forceinline__ void refill() {
         const bool take = n <= 32u;
-        const unsigned long long add = ((unsigned long long)nextw << 32) >> (n & 63u);
+        const unsigned long long add = ((unsigned long long)q0 << 32) >> (n & 63u);
         buf |= take ? add : 0ull;
         n += take ? 32u : 0u;
         k += take ? 1u : 0u;
-        const uint32_t eo = k < minw ? ib + k * stride : tb + k;
-        nextw = ldg_if(blk + eo, take && k < words, nextw);
+        q0 = take ? q1 : q0;
+        q1 = ldg_if(blk + eo(k + 1u), take && k + 1u < words, q1);
     }
     __device__ __forceinline__ uint32_t get(const uint16_t *lut) {
         uint32_t e = lut[(uint32_t)(buf >> (64 - kL))];
