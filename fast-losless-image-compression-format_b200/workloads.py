@@ -25,6 +25,29 @@ def gradient_noise(w, h, c, seed, sigma=4.0, alpha="opaque"):
     return img
 
 
+def gradient_noise_rows(w, h, c, seed, y0, y1, sigma=4.0, band=32):
+    """Rows [y0, y1) of a w x h gradient+noise image whose noise is seeded per 32-row band, so that
+    any rank can synthesise exactly its own block rows of one huge image (config C4) without
+    generating the rest.  Not the same pixels as gradient_noise(); same statistics."""
+    out = np.empty((y1 - y0, w, c), dtype=np.uint8)
+    x = np.arange(w, dtype=np.float32)[None, :]
+    for b0 in range(y0 - y0 % band, y1, band):
+        lo, hi = max(b0, y0), min(b0 + band, y1, h)
+        if hi <= lo:
+            continue
+        rng = np.random.default_rng([seed, b0 // band])
+        noise = rng.normal(0.0, sigma, size=(band, w, min(c, 3))).astype(np.float32)
+        y = np.arange(lo, hi, dtype=np.float32)[:, None]
+        ramp = 255.0 * (x + y) / max(w + h - 2, 1)
+        for ch in range(c):
+            if ch == 3:
+                out[lo - y0:hi - y0, :, 3] = 255
+                continue
+            base = ramp if ch != 1 else 255.0 - ramp
+            out[lo - y0:hi - y0, :, ch] = np.clip(base + noise[lo - b0:hi - b0, :, ch], 0, 255).astype(np.uint8)
+    return out
+
+
 def uniform_noise(w, h, c, seed):
     return np.random.default_rng(seed).integers(0, 256, size=(h, w, c), dtype=np.uint8)
 
