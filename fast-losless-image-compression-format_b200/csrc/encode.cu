@@ -429,7 +429,7 @@ __device__ __forceinline__ uint32_t gather_pairs(const uint32_t (&w)[4], int nv,
     return xs >> 16;
 }
 
-__global__ void __launch_bounds__(kEncThreads, 5) k_pack(const uint4 *__restrict__ resid, Geo g,
+__global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint4 *__restrict__ resid, Geo g,
                                                       const uint16_t *__restrict__ table,
                                                       uint32_t *__restrict__ streams, uint64_t capacity_words,
                                                       unsigned long long *status, unsigned long long *dirE,
