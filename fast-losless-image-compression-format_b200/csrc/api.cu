@@ -19,7 +19,7 @@ struct flic_ctx {
     // per-block workspace (grown on demand)
     uint64_t ws_blocks = 0;
     uint16_t *d_hist = nullptr, *d_table = nullptr;
-    uint4 *d_resid = nullptr;  // residual plane: 16 KB per block
+    uint32_t *d_resid = nullptr;  // residual plane: 32 rows x 32 lanes x C words (<= 16 KB) per block
     unsigned long long *d_status = nullptr, *d_dirE = nullptr;
     uint32_t *d_err = nullptr;
     uint32_t *h_err = nullptr;  // pinned

@@ -59,19 +59,6 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void *p) {
     return r;
 }
 
-// 16 bytes of a block row starting at byte `off`; bytes at or past `rb` read as 0.
-__device__ __forceinline__ uint4 load_chunk16(const uint8_t *row, int off, int rb, bool aligned) {
-    int nv = rb - off;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (nv <= 0) return v;
-    if (aligned && nv >= 16) return ldg_nc_v4(row + off);
-    uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-        if (j < nv) w[j >> 2] |= (uint32_t)__ldg(row + off + j) << (8 * (j & 3));
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
 // Packed byte-wise subtract-green for 3-channel data whose first byte has
 // channel phase `p` (0,1,2): ch0 bytes take the next byte (G), ch2 the previous.
 __device__ __forceinline__ uint32_t subgreen3(uint32_t prev, uint32_t cur, uint32_t next, int p) {
@@ -91,92 +78,69 @@ __device__ __forceinline__ uint32_t addgreen4(uint32_t px) {
     return __vadd4(px, g | (g << 16));
 }
 
-// Residual bytes [16*lane, 16*lane+16) of block row `r` (one warp spans the
-// row).  FLP0 §2: optional subtract-green, then pred = left pixel; at x == 0
-// the pixel above; at (0,0) zero — all inside the block.  Must be called by
-// all 32 lanes.  Returns the packed residuals; *nv = how many are real.
-__device__ __forceinline__ uint4 row_residuals(const uint8_t *pixels, const Geo &g, const BlockPos &p,
-                                               int r, int lane, int *nv) {
-    const uint8_t *row = pixels + (uint64_t)p.img * g.img_stride + (uint64_t)(p.y0 + r) * g.pitch +
-                         (uint64_t)p.x0 * g.c;
-    const int c = (int)g.c;
-    const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) && c >= 3;
-    uint4 v = load_chunk16(row, 16 * lane, (int)p.rb, g.aligned16 != 0);
-    *nv = max(0, min(16, (int)p.rb - 16 * lane));
+// ---- encode-side lane mapping -------------------------------------------------------------
+// One warp spans a block row; every lane owns exactly FOUR PIXELS of it, i.e. 4*C bytes = C
+// 32-bit words, for any channel count (so a 384-byte RGB row keeps all 32 lanes busy, and four
+// whole pixels per lane mean the colour transform never crosses a lane).
 
-    // transformed pixel above (lane 0 only), packed in the low c bytes
-    uint32_t up = 0;
-    if (lane == 0 && r > 0) {
-        const uint8_t *u = row - g.pitch;
-        uint32_t b0 = __ldg(u), b1 = c > 1 ? __ldg(u + 1) : 0u, b2 = c > 2 ? __ldg(u + 2) : 0u,
-                 b3 = c > 3 ? __ldg(u + 3) : 0u;
-        if (sg) { b0 = (b0 - b1) & 0xFFu; b2 = (b2 - b1) & 0xFFu; }
-        up = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-    }
-
-    if (sg) {
-        if (c == 4) {
-            v.x = subgreen4(v.x); v.y = subgreen4(v.y); v.z = subgreen4(v.z); v.w = subgreen4(v.w);
+// The lane's C words of block row `row` (pointer to the block row's first byte); pixels at or
+// past `bwa` read as 0.  *nv = how many of the lane's 4*C bytes are real.
+template <int C>
+__device__ __forceinline__ void load_lane_pixels(const uint8_t *row, int lane, int bwa, bool fast, uint32_t (&v)[C],
+                                                 int *nv) {
+    const int npx = max(0, min(4, bwa - 4 * lane));
+    *nv = npx * C;
+#pragma unroll
+    for (int j = 0; j < C; ++j) v[j] = 0;
+    if (fast && npx == 4) {  // 16-byte-aligned image: 4*C*lane is a multiple of C words
+        const uint8_t *p = row + 4 * C * lane;
+        if (C == 4) {
+            uint4 t = ldg_nc_v4(p);
+            v[0] = t.x; v[1 % C] = t.y; v[2 % C] = t.z; v[3 % C] = t.w;
+        } else if (C == 2) {
+            uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+            v[0] = t.x; v[1 % C] = t.y;
         } else {
-            uint32_t pw = __shfl_up_sync(0xFFFFFFFFu, v.w, 1);
-            uint32_t nw = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
-            int ph = lane % 3;  // (16*lane) % 3
-            uint4 t;
-            t.x = subgreen3(pw, v.x, v.y, ph);
-            t.y = subgreen3(v.x, v.y, v.z, (ph + 1) % 3);
-            t.z = subgreen3(v.y, v.z, v.w, (ph + 2) % 3);
-            t.w = subgreen3(v.z, v.w, nw, ph);
-            v = t;
+#pragma unroll
+            for (int j = 0; j < C; ++j) v[j] = __ldg(reinterpret_cast<const uint32_t *>(p) + j);
         }
+    } else {
+        const uint8_t *p = row + 4 * C * lane;
+#pragma unroll
+        for (int j = 0; j < 4 * C; ++j)
+            if (j < npx * C) v[j >> 2] |= (uint32_t)__ldg(p + j) << (8 * (j & 3));
     }
-
-    const int sh = 8 * (4 - c);
-    uint32_t pl = __shfl_up_sync(0xFFFFFFFFu, v.w, 1);
-    if (lane == 0) pl = up << sh;
-    uint4 res;
-    res.x = __vsub4(v.x, __funnelshift_r(pl, v.x, sh));
-    res.y = __vsub4(v.y, __funnelshift_r(v.x, v.y, sh));
-    res.z = __vsub4(v.z, __funnelshift_r(v.y, v.z, sh));
-    res.w = __vsub4(v.w, __funnelshift_r(v.z, v.w, sh));
-    return res;
 }
 
-// Fast path of row_residuals for a full-width (128-pixel) block row of a 16-byte-aligned image:
-// channels and the colour transform are compile-time, `row` already points at the lane's chunk.
+// Residual bytes of the lane's four pixels.  FLP0 §2: optional subtract-green, then pred = left
+// pixel; at x == 0 the pixel above (lane 0 passes it, transformed, in `up`); at (0,0) zero.
+// Must be called by all 32 lanes.
 template <int C, bool SG>
-__device__ __forceinline__ uint4 row_residuals_fast(const uint8_t *row, uint64_t pitch, int r, int lane, int *nv) {
-    constexpr int kLanes = kBW * C / 16;  // lanes that own bytes of the row
-    const bool own = lane < kLanes;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (own) v = ldg_nc_v4(row);
-    *nv = own ? 16 : 0;
-    uint32_t up = 0;
-    if (lane == 0 && r > 0) {
-        up = __ldg(reinterpret_cast<const uint32_t *>(row - pitch));  // 4-byte aligned: row is 16-byte aligned
-        if (C < 4) up &= (1u << (8 * (C & 3))) - 1u;
-        if (SG && C >= 3) up = subgreen4(up);  // bytes 0,2 minus byte 1; byte 3 (alpha or masked) untouched
-    }
+__device__ __forceinline__ void lane_residuals(uint32_t (&v)[C], uint32_t up, int lane, uint32_t (&res)[C]) {
     if (SG && C == 4) {
-        v.x = subgreen4(v.x); v.y = subgreen4(v.y); v.z = subgreen4(v.z); v.w = subgreen4(v.w);
-    } else if (SG && C == 3) {
-        const uint32_t pw = __shfl_up_sync(0xFFFFFFFFu, v.w, 1), nw = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
-        const int ph = lane % 3;
-        uint4 t;
-        t.x = subgreen3(pw, v.x, v.y, ph);
-        t.y = subgreen3(v.x, v.y, v.z, (ph + 1) % 3);
-        t.z = subgreen3(v.y, v.z, v.w, (ph + 2) % 3);
-        t.w = subgreen3(v.z, v.w, nw, ph);
-        v = t;
+#pragma unroll
+        for (int j = 0; j < C; ++j) v[j] = subgreen4(v[j]);
+    } else if (SG && C == 3) {  // 12 bytes = 4 whole pixels: word j starts at channel phase j, no lane crossing
+        const uint32_t a = v[0], b = v[1 % C], c = v[2 % C];
+        v[0] = subgreen3(0u, a, b, 0);
+        v[1 % C] = subgreen3(a, b, c, 1);
+        v[2 % C] = subgreen3(b, c, 0u, 2);
     }
     constexpr int sh = 8 * (4 - C);
-    uint32_t pl = __shfl_up_sync(0xFFFFFFFFu, v.w, 1);
+    uint32_t pl = __shfl_up_sync(0xFFFFFFFFu, v[C - 1], 1);
     if (lane == 0) pl = up << sh;
-    uint4 res;
-    res.x = __vsub4(v.x, __funnelshift_r(pl, v.x, sh));
-    res.y = __vsub4(v.y, __funnelshift_r(v.x, v.y, sh));
-    res.z = __vsub4(v.z, __funnelshift_r(v.y, v.z, sh));
-    res.w = __vsub4(v.w, __funnelshift_r(v.z, v.w, sh));
-    return res;
+    res[0] = __vsub4(v[0], __funnelshift_r(pl, v[0], sh));
+#pragma unroll
+    for (int j = 1; j < C; ++j) res[j] = __vsub4(v[j], __funnelshift_r(v[j - 1], v[j], sh));
+}
+
+// Transformed pixel above the block row's first pixel, packed in the low C bytes (lane 0 only).
+template <int C, bool SG>
+__device__ __forceinline__ uint32_t up_pixel(const uint8_t *row, uint64_t pitch) {
+    const uint8_t *u = row - pitch;
+    uint32_t b0 = __ldg(u), b1 = C > 1 ? __ldg(u + 1) : 0u, b2 = C > 2 ? __ldg(u + 2) : 0u, b3 = C > 3 ? __ldg(u + 3) : 0u;
+    if (SG && C >= 3) { b0 = (b0 - b1) & 0xFFu; b2 = (b2 - b1) & 0xFFu; }
+    return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
 }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
@@ -198,9 +162,9 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 // launchers (defined in the .cu files, used by api.cu)
-void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint4 *d_resid, cudaStream_t s);
+void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, cudaStream_t s);
 void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, cudaStream_t s);
-void launch_pack(const uint4 *d_resid, const Geo &g, const uint16_t *d_table, uint32_t *d_streams,
+void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, uint32_t *d_streams,
                  uint64_t capacity_words, unsigned long long *d_status, unsigned long long *d_dirE,
                  uint32_t *d_err, cudaStream_t s);
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,

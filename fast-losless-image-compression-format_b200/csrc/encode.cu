@@ -28,12 +28,12 @@ __device__ __forceinline__ uint32_t byte_x4(uint32_t w, int j) {
 constexpr int kEncThreads = 256;
 constexpr int kEncWarps = kEncThreads / 32;
 
-// resid (optional): the "residual plane" — per block a 32 x 512-byte tile of residual bytes in
-// 16-byte lane chunks — so that k_pack does not recompute prediction (the kernels are ALU-bound,
-// HBM has headroom: one extra N-byte write buys ~20 % of k_pack's instructions).
+// resid (optional): the "residual plane" — per block a tile [32 rows][32 lanes][C words] of residual
+// bytes in the lane order above — so that k_pack does not recompute prediction (the kernels are
+// ALU-bound, HBM has headroom: one extra N-byte write buys ~20 % of k_pack's instructions).
 template <int C, bool SG>
 __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__restrict__ pixels, Geo g,
-                                                            uint16_t *__restrict__ hist, uint4 *__restrict__ resid) {
+                                                            uint16_t *__restrict__ hist, uint32_t *__restrict__ resid) {
     __shared__ uint32_t sh[kEncWarps][256];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t gb = blockIdx.x;
@@ -41,42 +41,44 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
 
     for (int i = tid; i < kEncWarps * 256; i += kEncThreads) (&sh[0][0])[i] = 0;
 
-    uint4 res[kBH / kEncWarps];
+    uint32_t res[kBH / kEncWarps][C];
     int nv[kBH / kEncWarps];
-    if (g.aligned16 && p.bwa == (uint32_t)kBW) {  // block-uniform: full-width rows of an aligned image
-        const uint8_t *row = pixels + (uint64_t)p.img * g.img_stride + (uint64_t)(p.y0 + warp) * g.pitch +
-                             (uint64_t)p.x0 * C + 16 * lane;
+    const bool fast = g.aligned16 != 0;
+    const uint8_t *row = pixels + (uint64_t)p.img * g.img_stride + (uint64_t)(p.y0 + warp) * g.pitch + (uint64_t)p.x0 * C;
 #pragma unroll
-        for (int q = 0; q < kBH / kEncWarps; ++q) {
-            const int r = warp + kEncWarps * q;
-            nv[q] = 0;
-            res[q] = make_uint4(0, 0, 0, 0);
-            if (r < (int)p.bha) res[q] = row_residuals_fast<C, SG>(row, g.pitch, r, lane, &nv[q]);  // warp-uniform
-            if (resid) resid[(gb * kBH + r) * 32 + lane] = res[q];
-            row += kEncWarps * g.pitch;
-        }
-    } else {
+    for (int q = 0; q < kBH / kEncWarps; ++q) {
+        const int r = warp + kEncWarps * q;
+        nv[q] = 0;
 #pragma unroll
-        for (int q = 0; q < kBH / kEncWarps; ++q) {
-            const int r = warp + kEncWarps * q;
-            nv[q] = 0;
-            res[q] = make_uint4(0, 0, 0, 0);
-            if (r < (int)p.bha) res[q] = row_residuals(pixels, g, p, r, lane, &nv[q]);
-            if (resid) resid[(gb * kBH + r) * 32 + lane] = res[q];
+        for (int j = 0; j < C; ++j) res[q][j] = 0;
+        if (r < (int)p.bha) {  // warp-uniform
+            uint32_t v[C];
+            load_lane_pixels<C>(row, lane, (int)p.bwa, fast, v, &nv[q]);
+            const uint32_t up = (lane == 0 && r > 0) ? up_pixel<C, SG>(row, g.pitch) : 0u;
+            lane_residuals<C, SG>(v, up, lane, res[q]);
         }
+        if (resid) {
+            uint32_t *t = resid + ((gb * kBH + r) * 32 + lane) * C;
+            if (C == 4) *reinterpret_cast<uint4 *>(t) = make_uint4(res[q][0], res[q][1 % C], res[q][2 % C], res[q][3 % C]);
+            else if (C == 2) *reinterpret_cast<uint2 *>(t) = make_uint2(res[q][0], res[q][1 % C]);
+            else {
+#pragma unroll
+                for (int j = 0; j < C; ++j) t[j] = res[q][j];
+            }
+        }
+        row += kEncWarps * g.pitch;
     }
     __syncthreads();
     char *my = reinterpret_cast<char *>(sh[warp]);
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
-        const uint32_t w[4] = {res[q].x, res[q].y, res[q].z, res[q].w};
-        if (nv[q] == 16) {
+        if (nv[q] == 4 * C) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(w[j >> 2], j & 3)), 1u);
+            for (int j = 0; j < 4 * C; ++j) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[q][j >> 2], j & 3)), 1u);
         } else if (nv[q] > 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (j < nv[q]) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(w[j >> 2], j & 3)), 1u);
+            for (int j = 0; j < 4 * C; ++j)
+                if (j < nv[q]) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[q][j >> 2], j & 3)), 1u);
         }
     }
     __syncthreads();
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
     hist[gb * 256 + tid] = (uint16_t)s;
 }
 
-void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint4 *d_resid, cudaStream_t s) {
+void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) && g.c >= 3;
     const unsigned grid = (unsigned)total;
@@ -405,16 +407,16 @@ __device__ __forceinline__ uint32_t byte_x8(uint32_t w, int j) {
     return j == 0 ? (w << 3) & 0x7F8u : (w >> (8 * j - 3)) & 0x7F8u;
 }
 
-// Looks up the lane's 16 symbols and merges them pairwise on the FMA pipe: a table entry is
+// Looks up the lane's 4*C symbols and merges them pairwise on the FMA pipe: a table entry is
 // {code, len << 16 | 2^len}, so (code0 << len1) | code1 is one IMAD.  pc[i] = code bits of
 // symbols 2i,2i+1 (at most 22), pl[i] = their bit count.  Returns the lane's total bit count.
-template <bool kFull>
-__device__ __forceinline__ uint32_t gather_pairs(const uint32_t (&w)[4], int nv, const uint2 *tab, uint32_t (&pc)[8],
-                                                 uint32_t (&pl)[8]) {
+template <int C, bool kFull>
+__device__ __forceinline__ uint32_t gather_pairs(const uint32_t (&w)[C], int nv, const uint2 *tab, uint32_t (&pc)[2 * C],
+                                                 uint32_t (&pl)[2 * C]) {
     const char *t = reinterpret_cast<const char *>(tab);
     uint32_t xs = 0;
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
+    for (int j = 0; j < 4 * C; j += 2) {
         uint2 e0 = *reinterpret_cast<const uint2 *>(t + byte_x8(w[j >> 2], j & 3));
         uint2 e1 = *reinterpret_cast<const uint2 *>(t + byte_x8(w[j >> 2], (j & 3) + 1));
         if (!kFull) {
@@ -429,7 +431,8 @@ __device__ __forceinline__ uint32_t gather_pairs(const uint32_t (&w)[4], int nv,
     return xs >> 16;
 }
 
-__global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint4 *__restrict__ resid, Geo g,
+template <int C>
+__global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restrict__ resid, Geo g,
                                                       const uint16_t *__restrict__ table,
                                                       uint32_t *__restrict__ streams, uint64_t capacity_words,
                                                       unsigned long long *status, unsigned long long *dirE,
@@ -460,25 +463,34 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint4 *__restrict
         if (l == kLenSole) l = 0;
         tab[tid] = make_uint2(l ? (e & 0xFFFu) : 0u, (l << 16) | (1u << l));
     }
-    uint4 res[kBH / kEncWarps];
+    uint32_t res[kBH / kEncWarps][C];
     int nv[kBH / kEncWarps];
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
         const int r = warp + kEncWarps * q;
-        nv[q] = r < (int)p.bha ? max(0, min(16, (int)p.rb - 16 * lane)) : 0;
-        res[q] = ldg_nc_v4(resid + (gb * kBH + r) * 32 + lane);
+        nv[q] = r < (int)p.bha ? C * max(0, min(4, (int)p.bwa - 4 * lane)) : 0;
+        const uint32_t *t = resid + ((gb * kBH + r) * 32 + lane) * C;
+        if (C == 4) {
+            uint4 v = ldg_nc_v4(t);
+            res[q][0] = v.x; res[q][1 % C] = v.y; res[q][2 % C] = v.z; res[q][3 % C] = v.w;
+        } else if (C == 2) {
+            uint2 v = __ldg(reinterpret_cast<const uint2 *>(t));
+            res[q][0] = v.x; res[q][1 % C] = v.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < C; ++j) res[q][j] = __ldg(t + j);
+        }
     }
     __syncthreads();
 
-    // FLP0 §5: one warp per row.  Each lane merges its 16 codes pairwise, a warp scan of bit counts
+    // FLP0 §5: one warp per row.  Each lane merges its 4*C codes pairwise, a warp scan of bit counts
     // places them, and 32-bit words are OR-ed into the zeroed staging row.
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
         const int r = warp + kEncWarps * q;
-        const uint32_t w[4] = {res[q].x, res[q].y, res[q].z, res[q].w};
-        uint32_t pc[8], pl[8], nbits;
-        if (nv[q] == 16) nbits = gather_pairs<true>(w, 16, tab, pc, pl);
-        else nbits = gather_pairs<false>(w, nv[q], tab, pc, pl);  // ragged edge / lanes past the row: zero-length entries
+        uint32_t pc[2 * C], pl[2 * C], nbits;
+        if (nv[q] == 4 * C) nbits = gather_pairs<C, true>(res[q], 4 * C, tab, pc, pl);
+        else nbits = gather_pairs<C, false>(res[q], nv[q], tab, pc, pl);  // ragged edge / lanes past the row
         const uint32_t incl = warp_incl_scan(nbits, lane);
         if (lane == 31) rwc[r] = (incl + 31u) >> 5;
         const uint32_t o = incl - nbits;
@@ -489,7 +501,7 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint4 *__restrict
         // issued unconditionally (a zero when there is nothing to flush): straight-line code, no branches.
         uint32_t acc = 0, na = o & 31u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 2 * C; ++i) {
             const unsigned long long a64 = ((unsigned long long)acc << pl[i]) | pc[i];
             na += pl[i];
             const bool flush = na >= 32u;
@@ -560,12 +572,19 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint4 *__restrict
     }
 }
 
-void launch_pack(const uint4 *d_resid, const Geo &g, const uint16_t *d_table, uint32_t *d_streams,
+void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, uint32_t *d_streams,
                  uint64_t capacity_words, unsigned long long *d_status, unsigned long long *d_dirE,
                  uint32_t *d_err, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;  // caller has zeroed d_status[0..total] on this stream
-    k_pack<<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_streams, capacity_words, d_status,
-                                                  d_dirE, d_err);
+#define FLIC_PACK(C) \
+    k_pack<C><<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_streams, capacity_words, d_status, d_dirE, d_err)
+    switch (g.c) {
+        case 1: FLIC_PACK(1); break;
+        case 2: FLIC_PACK(2); break;
+        case 3: FLIC_PACK(3); break;
+        default: FLIC_PACK(4); break;
+    }
+#undef FLIC_PACK
 }
 
 // ------------------------------------------------------------------ k_finalize
