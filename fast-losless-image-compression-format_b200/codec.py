@@ -11,7 +11,7 @@ import numpy as np
 
 from .build import library_path
 
-BLOCK_W, BLOCK_H, MAX_CODE_LEN = 128, 32, 11
+BLOCK_W, BLOCK_H, MAX_CODE_LEN = 128, 32, 10
 PRED_LEFT, FLAG_SUBGREEN = 1, 0x10
 
 _ERR = {

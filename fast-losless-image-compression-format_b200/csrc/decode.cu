@@ -3,11 +3,11 @@
 // One WARP per block, one LANE per row sub-stream (the format stores 32 word-
 // aligned row streams per block precisely so that a warp has 32 independent
 // bit-serial decodes in flight).  Per warp: read the 128-byte length table,
-// rebuild canonical codes with a packed-counter warp scan, fill a 2^11-entry
+// rebuild canonical codes with a packed-counter warp scan, fill a 2^kL-entry
 // shared-memory LUT (cooperatively for short codes, per lane for long ones),
 // exclusive-scan the row word counts into per-lane stream offsets, then every
 // lane runs a branch-light LUT decode with a 64-bit MSB-first bit buffer
-// (one refill per 2 symbols), undoes the left predictor in registers and
+// (one refill per 32/kL symbols), undoes the left predictor in registers and
 // emits 16-byte vector stores.  Column 0 is a byte-wise prefix sum down the
 // rows, done as a warp scan.
 //
@@ -17,6 +17,8 @@
 namespace flic {
 
 constexpr int kDecWarps = 4;
+// a one-word refill guarantees 32 buffered bits: that is floor(32 / kL) whole symbols
+constexpr int kSymsPerRefill = 32 / kL;
 
 // predicated 32-bit read-only load: `old` is kept when pred is false (no branch, no access)
 __device__ __forceinline__ uint32_t ldg_if(const uint32_t *p, bool pred, uint32_t old) {
@@ -46,8 +48,8 @@ struct BitReader {
         q0 = ldg_if(blk + eo(0), 0u < words, 0u);
         q1 = ldg_if(blk + eo(1), 1u < words, 0u);
     }
-    // afterwards n >= 32 (exactly 32 when the buffer had run dry), i.e. two 11-bit symbols are
-    // always buffered — three would need 33 bits, so the decoder refills every second symbol
+    // afterwards n >= 32 (exactly 32 when the buffer had run dry), i.e. kSymsPerRefill = 32 / kL
+    // symbols are always buffered; the decoder refills that often (every 3rd symbol at kL = 10)
     __device__ __forceinline__ void refill() {
         const bool take = n <= 32u;
         const unsigned long long add = ((unsigned long long)q0 << 32) >> (n & 63u);
@@ -185,7 +187,7 @@ __device__ __forceinline__ uint32_t decode_pixel(BitReader &br, const uint16_t *
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) {
         if (phase == 0) br.refill();
-        phase ^= 1;
+        phase = phase == kSymsPerRefill - 1 ? 0 : phase + 1;
         r |= br.get(lut) << (8 * ch);
     }
     return r;

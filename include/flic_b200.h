@@ -39,7 +39,7 @@ extern "C" {
 
 #define FLIC_BLOCK_W 128        /* pixels per block row   (one CTA / one decode warp per block) */
 #define FLIC_BLOCK_H 32         /* rows per block         (one decode lane per row sub-stream)  */
-#define FLIC_MAX_CODE_LEN 11
+#define FLIC_MAX_CODE_LEN 10
 #define FLIC_HEADER_BYTES 32
 
 #define FLIC_PRED_LEFT 1u       /* flags bits 0-3: predictor id */

@@ -28,7 +28,7 @@ extern "C" {
 
 #define FLP0_MAGIC 0x30504C46u /* 'F','L','P','0' little-endian */
 #define FLP0_VERSION 2
-#define FLP0_MAX_CODE_LEN 11
+#define FLP0_MAX_CODE_LEN 10
 #define FLP0_LEN_SOLE 15 /* nibble value: the block's only symbol, zero-length code */
 #define FLP0_HEADER_BYTES 32
 

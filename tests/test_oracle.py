@@ -54,7 +54,7 @@ def test_known_answer_lengths(oracle):
 
 
 def test_length_limit_and_kraft(oracle):
-    """Fibonacci counts force depth > 11; the repair must keep Kraft equality and the cap."""
+    """Fibonacci counts force depth > 10; the repair must keep Kraft equality and the cap."""
     fib = [1, 1]
     while len(fib) < 20:
         fib.append(fib[-1] + fib[-2])
@@ -62,8 +62,8 @@ def test_length_limit_and_kraft(oracle):
     h[:20] = fib
     ln = oracle.lengths(h).astype(int)
     used = ln[ln > 0]
-    assert used.max() == 11
-    assert sum(2 ** (11 - l) for l in used) == 2 ** 11
+    assert used.max() == 10
+    assert sum(2 ** (10 - l) for l in used) == 2 ** 10
     # rarer symbols never get shorter codes than more frequent ones
     order = np.argsort(h[:20], kind="stable")
     assert all(ln[order[i]] >= ln[order[i + 1]] for i in range(19))
@@ -73,14 +73,14 @@ def test_length_limit_and_kraft(oracle):
         ln = oracle.lengths(h).astype(int)
         used = ln[(ln > 0) & (ln != 15)]
         if used.size:
-            assert used.max() <= 11 and sum(2 ** (11 - l) for l in used) == 2 ** 11
+            assert used.max() <= 11 and sum(2 ** (10 - l) for l in used) == 2 ** 10
 
 
 def test_canonical_codes_prefix_free(oracle):
     rng = np.random.default_rng(1)
     h = rng.integers(0, 500, 256).astype(np.uint32)
     t = oracle.table(h).astype(int)
-    codes = sorted((format(e & 0xFFF, "b").zfill(e >> 12) for e in t if 1 <= (e >> 12) <= 11))
+    codes = sorted((format(e & 0xFFF, "b").zfill(e >> 12) for e in t if 1 <= (e >> 12) <= 10))
     assert all(not b.startswith(a) for a, b in zip(codes, codes[1:]))
 
 
