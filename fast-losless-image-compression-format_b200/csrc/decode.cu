@@ -31,42 +31,91 @@ __device__ __forceinline__ uint32_t ldg_if(const uint32_t *p, bool pred, uint32_
 
 // MSB-first reader over one row sub-stream laid out per FLP0 §6: words k < minw sit in the
 // block's interleaved region (word k of row r at k*stride + r), the rest in the row's tail.
-// Two stream words are always queued in registers (q0 = word k, q1 = word k+1): a word is
-// requested four symbols before it is used, which rides out an L1 miss; refill() is
-// straight-line code with one predicated load.
+//
+// The loop is built around what the ALU pipe (LOP3/SHF/IADD, half rate on sm_100) has to do per
+// symbol, which is what bounds this kernel:
+//   * the 64-bit bit buffer is two registers, valid bits at the top of hi, zeros below them;
+//   * a LUT entry is  len | symbol << 8 : the funnel shifts that consume a symbol read their
+//     count from the entry's low 5 bits (wrap mode), so the length is never extracted;
+//   * `cn` counts buffered bits in its low byte and is updated as cn -= entry (the symbol byte
+//     only disturbs bits 8 and up); "needs a refill" is a single bit test, cn & 32 == 0;
+//   * the LUT address is (hi >> 21) & 0x7FE | lut: the shift is issued as IMAD.HI on the FMA
+//     pipe, the mask-and-base is one LOP3 (the warp's LUT is 2 KB-aligned in shared memory);
+//   * a refill is straight-line predicated code; one stream word is always queued in `wq`.
 struct BitReader {
-    const uint32_t *blk;          // block payload (warp-uniform)
-    uint32_t ib, stride, tb;      // element offsets: interleaved base, stride, tail base (pre-biased by -minw)
-    uint32_t minw, words, k;      // k = index of the word held in q0
-    uint32_t q0, q1, n;
-    unsigned long long buf;
-    __device__ __forceinline__ uint32_t eo(uint32_t i) const { return i < minw ? ib + i * stride : tb + i; }
-    __device__ __forceinline__ void init(const uint32_t *b, uint32_t ib_, uint32_t stride_, uint32_t tb_,
-                                         uint32_t minw_, uint32_t words_) {
-        blk = b; ib = ib_; stride = stride_; tb = tb_; minw = minw_; words = words_;
-        k = 0; n = 0; buf = 0;
-        q0 = ldg_if(blk + eo(0), 0u < words, 0u);
-        q1 = ldg_if(blk + eo(1), 1u < words, 0u);
-    }
-    // afterwards n >= 32 (exactly 32 when the buffer had run dry), i.e. kSymsPerRefill = 32 / kL
-    // symbols are always buffered; the decoder refills that often (every 3rd symbol at kL = 10)
-    __device__ __forceinline__ void refill() {
-        const bool take = n <= 32u;
-        const unsigned long long add = ((unsigned long long)q0 << 32) >> (n & 63u);
-        buf |= take ? add : 0ull;
-        n += take ? 32u : 0u;
-        k += take ? 1u : 0u;
-        q0 = take ? q1 : q0;
-        q1 = ldg_if(blk + eo(k + 1u), take && k + 1u < words, q1);
-    }
-    __device__ __forceinline__ uint32_t get(const uint16_t *lut) {
-        uint32_t e = lut[(uint32_t)(buf >> (64 - kL))];
-        uint32_t l = e >> 8;
-        buf <<= l;
-        n -= l;
-        return e & 0xFFu;
-    }
+    uint32_t hi, lo;  // bit buffer
+    uint32_t cn;      // low byte: number of buffered bits (0..63)
+    uint32_t wq;      // next stream word (index k - 1), already loaded
+    uint32_t k;       // index of the word after wq
 };
+
+struct RowStream {
+    const uint32_t *blk;     // block payload (warp-uniform)
+    uint32_t ib, stride, tb; // element offsets: interleaved base, stride, tail base (pre-biased by -minw)
+    uint32_t minw, words;
+    __device__ __forceinline__ uint32_t eo(uint32_t i) const { return i < minw ? ib + i * stride : tb + i; }
+};
+
+__device__ __forceinline__ void reader_init(BitReader &r, const RowStream &rs) {
+    r.hi = r.lo = 0; r.cn = 0; r.k = 1;
+    r.wq = ldg_if(rs.blk + rs.eo(0), 0u < rs.words, 0u);
+}
+
+// After this at least 32 bits are buffered, i.e. kSymsPerRefill = 32 / kL whole symbols.
+// kFast: every word this chunk can touch lies in the interleaved region (checked by the caller
+// with one vote per chunk), so the address is one IMAD and there is no bounds test.
+template <bool kFast>
+__device__ __forceinline__ void refill(BitReader &r, const RowStream &rs) {
+    // Straight-line, predicated (hand-scheduled in PTX so that it stays six ALU operations):
+    //   take = (cn & 32) == 0          fewer than 32 bits buffered, so lo is empty
+    //   hi  |= wq >> n;  lo = wq << (32 - n)   (funnel shifts in wrap mode read n from cn's low 5 bits;
+    //                                           n == 0 gives lo = 0)
+    //   cn  += 32;  wq = next word;  k += 1
+    if (kFast) {
+        const uint32_t *p = rs.blk + (rs.ib + r.k * rs.stride);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+            "and.b32 t, %2, 32;\n\t"
+            "setp.eq.u32 p, t, 0;\n\t"
+            "@p shf.r.wrap.b32 t, %3, 0, %2;\n\t"
+            "@p or.b32 %0, %0, t;\n\t"
+            "@p shf.r.wrap.b32 %1, 0, %3, %2;\n\t"
+            "@p add.u32 %2, %2, 32;\n\t"
+            "@p ld.global.nc.u32 %3, [%5];\n\t"
+            "@p add.u32 %4, %4, 1;\n\t}"
+            : "+r"(r.hi), "+r"(r.lo), "+r"(r.cn), "+r"(r.wq), "+r"(r.k)
+            : "l"(p));
+    } else {
+        const uint32_t *p = rs.blk + rs.eo(r.k);
+        const uint32_t in = r.k < rs.words;  // past the row's last word the stream reads as zeros
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t.reg .b32 t;\n\t"
+            "and.b32 t, %2, 32;\n\t"
+            "setp.eq.u32 p, t, 0;\n\t"
+            "setp.ne.and.u32 q, %6, 0, p;\n\t"
+            "@p shf.r.wrap.b32 t, %3, 0, %2;\n\t"
+            "@p or.b32 %0, %0, t;\n\t"
+            "@p shf.r.wrap.b32 %1, 0, %3, %2;\n\t"
+            "@p add.u32 %2, %2, 32;\n\t"
+            "@p mov.u32 %3, 0;\n\t"
+            "@q ld.global.nc.u32 %3, [%5];\n\t"
+            "@p add.u32 %4, %4, 1;\n\t}"
+            : "+r"(r.hi), "+r"(r.lo), "+r"(r.cn), "+r"(r.wq), "+r"(r.k)
+            : "l"(p), "r"(in));
+    }
+}
+
+// Decodes one symbol; returns the LUT entry (len | sym << 8).  `luts` is the CTA's LUT array,
+// `wsel` = warp << 11 selects the warp's 2 KB table, `m2048` is the constant 2048 kept opaque
+// (a kernel argument) so that the shift is issued as IMAD.HI.
+__device__ __forceinline__ uint32_t get(BitReader &r, const char *luts, uint32_t wsel, uint32_t m2048) {
+    const uint32_t o = (__umulhi(r.hi, m2048) & 0x7FEu) | wsel;
+    const uint32_t e = *reinterpret_cast<const uint16_t *>(luts + o);
+    r.hi = __funnelshift_l(r.lo, r.hi, e);
+    r.lo = __funnelshift_l(0u, r.lo, e);
+    r.cn -= e;
+    return e;
+}
 
 __device__ __forceinline__ uint64_t shfl_up64d(uint64_t v, int d) {
     uint32_t lo = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)v, d);
@@ -121,7 +170,7 @@ __device__ bool build_lut(uint16_t *lut, uint32_t nibw, int lane) {
         // one symbol, zero-length code: every LUT entry yields it and consumes nothing
         uint32_t sym = (uint32_t)__shfl_sync(0xFFFFFFFFu, sole, __ffs(solem) - 1);
         uint32_t *l32 = reinterpret_cast<uint32_t *>(lut);
-        for (int i = lane; i < kLutSize / 2; i += 32) l32[i] = sym | (sym << 16);
+        for (int i = lane; i < kLutSize / 2; i += 32) l32[i] = (sym << 8) | (sym << 24);
         __syncwarp();
         return !__any_sync(0xFFFFFFFFu, bad);
     }
@@ -151,7 +200,7 @@ __device__ bool build_lut(uint16_t *lut, uint32_t nibw, int lane) {
                 cntd_add(ea, eb, l);
                 start[k] = code << (kL - l);
                 span[k] = 1u << (kL - l);
-                ent[k] = (uint32_t)(8 * lane + k) | (l << 8);
+                ent[k] = ((uint32_t)(8 * lane + k) << 8) | l;
                 if (start[k] + span[k] > (uint32_t)kLutSize) { bad = true; span[k] = 0; }
             }
         }
@@ -181,22 +230,52 @@ __device__ bool build_lut(uint16_t *lut, uint32_t nibw, int lane) {
     return !__any_sync(0xFFFFFFFFu, bad);
 }
 
-template <int C>
-__device__ __forceinline__ uint32_t decode_pixel(BitReader &br, const uint16_t *lut, int &phase) {
-    uint32_t r = 0;
-#pragma unroll
-    for (int ch = 0; ch < C; ++ch) {
-        if (phase == 0) br.refill();
-        phase = phase == kSymsPerRefill - 1 ? 0 : phase + 1;
-        r |= br.get(lut) << (8 * ch);
-    }
-    return r;
-}
+// ---- per-lane pixel reconstruction ------------------------------------------------------------
+// Left prediction is a running byte-wise sum along the row.  The running values live in two
+// registers with 16-bit lanes, A = (ch0, ch2) and B = (ch1, ch3), each value in the HIGH byte of
+// its half: adding a raw LUT entry (len | sym << 8) advances the value, and the length lands in
+// the low byte, where it is junk that is masked off once per chunk (before it can carry).
+struct Acc { uint32_t a, b; };
 
 template <int C>
-__device__ __forceinline__ uint32_t untransform(uint32_t t, bool sg) {
-    if (C >= 3 && sg) t = addgreen4(t);
-    return t;
+__device__ __forceinline__ void acc_add(Acc &v, int ch, uint32_t e) {
+    if (ch == 0) v.a += e;
+    else if (ch == 1) v.b += e;
+    else if (ch == 2) v.a = e * 65536u + v.a;
+    else v.b = e * 65536u + v.b;
+}
+__device__ __forceinline__ void acc_clean(Acc &v) { v.a &= 0xFF00FF00u; v.b &= 0xFF00FF00u; }
+
+// accumulators holding packed (transformed) pixel t
+template <int C>
+__device__ __forceinline__ Acc acc_from(uint32_t t) {
+    Acc v;
+    v.a = __byte_perm(t, 0u, 0x2404);  // [0, t.b0, 0, t.b2]
+    v.b = __byte_perm(t, 0u, 0x3414);  // [0, t.b1, 0, t.b3]
+    return v;
+}
+// the C bytes of the current pixel in the low bytes (colour transform undone); bytes above C are junk
+template <int C, bool SG>
+__device__ __forceinline__ uint32_t acc_pixel(const Acc &v) {
+    uint32_t a = v.a;
+    if (SG && C >= 3) a += __byte_perm(v.b, 0u, 0x1414);  // R += G, B += G (carries only reach junk bytes)
+    return __byte_perm(a, v.b, 0x7351);                   // [a.b1, b.b1, a.b3, b.b3]
+}
+
+// four pixels (C valid low bytes each) -> C output words
+template <int C>
+__device__ __forceinline__ void pack4(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t *o) {
+    if (C == 4) { o[0] = p0; o[1] = p1; o[2] = p2; o[3] = p3; }
+    else if (C == 3) {
+        o[0] = __byte_perm(p0, p1, 0x4210);
+        o[1] = __byte_perm(p1, p2, 0x5421);
+        o[2] = __byte_perm(p2, p3, 0x6542);
+    } else if (C == 2) {
+        o[0] = __byte_perm(p0, p1, 0x5410);
+        o[1] = __byte_perm(p2, p3, 0x5410);
+    } else {
+        o[0] = __byte_perm(__byte_perm(p0, p1, 0x0040), __byte_perm(p2, p3, 0x0040), 0x5410);
+    }
 }
 
 template <int C>
@@ -205,39 +284,76 @@ __device__ __forceinline__ void store_bytes(uint8_t *dst, uint32_t px) {
     for (int ch = 0; ch < C; ++ch) dst[ch] = (uint8_t)(px >> (8 * ch));
 }
 
-// U pixels fill a whole number of 16-byte chunks: C=1:16, 2:8, 3:16, 4:4
-template <int C> struct Unroll { static constexpr int U = (C == 4) ? 4 : (C == 2 ? 8 : 16); };
+// U pixels per chunk fill whole 16-byte stores (two for RGBA: a full 32-byte sector)
+template <int C> struct Chunk {
+    static constexpr int U = (C == 4) ? 8 : (C == 2 ? 8 : 16);
+    static constexpr int W = U * C / 4;                          // words per chunk
+    static constexpr int kMaxRefills = (U * C * kL + 31) / 32 + 1;  // words a chunk can request
+};
 
-template <int C>
-__device__ void decode_rows(BitReader &br, const uint16_t *lut, uint8_t *dst, int bwa, bool active, bool sg,
-                            bool aligned, int lane) {
-    constexpr int U = Unroll<C>::U;
-    constexpr int W = U * C / 4;  // words per chunk
-    constexpr uint32_t cmask = C == 4 ? 0xFFFFFFFFu : ((1u << (8 * (C & 3))) - 1u);
-    // column 0: residual against the pixel above == byte-wise prefix sum down the rows
-    int phase = 0;
-    uint32_t cur = active ? decode_pixel<C>(br, lut, phase) : 0u;
+// One chunk of U pixels: U*C symbols with a refill check before every kSymsPerRefill-th.
+template <int C, bool SG, bool kFast>
+__device__ __forceinline__ void decode_chunk(BitReader &br, const RowStream &rs, Acc &acc, const char *luts,
+                                             uint32_t wsel, uint32_t m2048, uint32_t *o) {
+    constexpr int U = Chunk<C>::U;
+#pragma unroll
+    for (int g = 0; g < U / 4; ++g) {
+        uint32_t px[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+                if (((g * 4 + u) * C + ch) % kSymsPerRefill == 0) refill<kFast>(br, rs);
+                acc_add<C>(acc, ch, get(br, luts, wsel, m2048));
+            }
+            px[u] = acc_pixel<C, SG>(acc);
+        }
+        pack4<C>(px[0], px[1], px[2], px[3], o + g * C);
+    }
+    acc_clean(acc);
+}
+
+template <int C, bool SG>
+__device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel, uint32_t m2048, uint8_t *dst, int bwa,
+                            bool active, bool aligned, int lane) {
+    constexpr int U = Chunk<C>::U, W = Chunk<C>::W;
+    const uint32_t amask = __ballot_sync(0xFFFFFFFFu, active);
+    BitReader br;
+    reader_init(br, rs);
+    // Column 0 is predicted from the pixel above: its value is a byte-wise prefix sum of the rows'
+    // first residuals.  Decode that one pixel on a COPY of the reader, scan, and start the row's
+    // running sum from the value above; the main loop then decodes the row from x = 0 uniformly.
+    uint32_t first = 0;
+    if (active) {
+        BitReader t = br;
+        Acc z = {0u, 0u};
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            if (ch % kSymsPerRefill == 0) refill<false>(t, rs);
+            acc_add<C>(z, ch, get(t, luts, wsel, m2048));
+        }
+        first = __byte_perm(z.a, z.b, 0x7351);
+        if (C < 4) first &= (1u << (8 * (C & 3))) - 1u;
+    }
+    uint32_t incl = first;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, cur, d);
-        if (lane >= d) cur = __vadd4(cur, t);
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl = __vadd4(incl, t);
     }
+    uint32_t above = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+    if (lane == 0) above = 0;
     if (!active) return;
+    Acc acc = acc_from<C>(above);
 
     int x = 0;
     for (; x + U <= bwa; x += U) {
         uint32_t o[W];
-#pragma unroll
-        for (int i = 0; i < W; ++i) o[i] = 0;
-        phase = 0;  // chunk boundary: always refill first
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (u > 0 || x > 0) cur = __vadd4(cur, decode_pixel<C>(br, lut, phase));
-            uint32_t px = untransform<C>(cur, sg) & cmask;
-            const int bp = u * C;
-            o[bp >> 2] |= px << (8 * (bp & 3));
-            if ((bp & 3) + C > 4) o[(bp >> 2) + 1] |= px >> (8 * (4 - (bp & 3)));
-        }
+        // fast path while no lane of the warp can leave the interleaved region inside this chunk
+        if (__all_sync(amask, br.k + (uint32_t)Chunk<C>::kMaxRefills <= rs.minw))
+            decode_chunk<C, SG, true>(br, rs, acc, luts, wsel, m2048, o);
+        else
+            decode_chunk<C, SG, false>(br, rs, acc, luts, wsel, m2048, o);
         uint8_t *d = dst + (size_t)x * C;
         if (aligned) {
 #pragma unroll
@@ -250,15 +366,19 @@ __device__ void decode_rows(BitReader &br, const uint16_t *lut, uint8_t *dst, in
     }
     // ragged right edge of the image
     for (; x < bwa; ++x) {
-        phase = 0;
-        if (x > 0) cur = __vadd4(cur, decode_pixel<C>(br, lut, phase));
-        store_bytes<C>(dst + (size_t)x * C, untransform<C>(cur, sg));
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            if (ch % kSymsPerRefill == 0) refill<false>(br, rs);
+            acc_add<C>(acc, ch, get(br, luts, wsel, m2048));
+        }
+        store_bytes<C>(dst + (size_t)x * C, acc_pixel<C, SG>(acc));
+        acc_clean(acc);
     }
 }
 
 __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *__restrict__ streams,
                                                           const unsigned long long *__restrict__ offsets, Geo g,
-                                                          uint8_t *__restrict__ pixels, uint32_t *err) {
+                                                          uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048) {
     __shared__ __align__(16) uint16_t luts[kDecWarps][kLutSize];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t gb = (uint64_t)blockIdx.x * kDecWarps + warp;
@@ -299,18 +419,28 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
         if (lane == 0) atomicOr(err, kErrFormat);
         return;
     }
-    BitReader br;
-    br.init(blk, kBlkHdrWords + lane, p.bha, kBlkHdrWords + minw * p.bha + (incl - rc) - lane * minw - minw, minw,
-            active ? rc : 0u);
+    RowStream rs;
+    rs.blk = blk; rs.ib = kBlkHdrWords + lane; rs.stride = p.bha;
+    rs.tb = kBlkHdrWords + minw * p.bha + (incl - rc) - lane * minw - minw;
+    rs.minw = minw; rs.words = active ? rc : 0u;
     uint8_t *dst = pixels + (uint64_t)p.img * g.img_stride + (uint64_t)(p.y0 + lane) * g.pitch +
                    (uint64_t)p.x0 * g.c;
-    const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) != 0;
+    const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) != 0 && g.c >= 3;
     const bool aligned = g.aligned16 != 0;
+    const char *lb = reinterpret_cast<const char *>(&luts[0][0]);
+    const uint32_t wsel = (uint32_t)warp << 11;
+    static_assert(kLutSize * 2 == 2048, "wsel assumes 2 KB per warp LUT");
     switch (g.c) {
-        case 1: decode_rows<1>(br, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
-        case 2: decode_rows<2>(br, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
-        case 3: decode_rows<3>(br, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
-        default: decode_rows<4>(br, lut, dst, (int)p.bwa, active, sg, aligned, lane); break;
+        case 1: decode_rows<1, false>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane); break;
+        case 2: decode_rows<2, false>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane); break;
+        case 3:
+            if (sg) decode_rows<3, true>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane);
+            else decode_rows<3, false>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane);
+            break;
+        default:
+            if (sg) decode_rows<4, true>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane);
+            else decode_rows<4, false>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane);
+            break;
     }
 }
 
@@ -318,7 +448,7 @@ void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offset
                    uint8_t *d_pixels, uint32_t *d_err, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
     unsigned grid = (unsigned)((total + kDecWarps - 1) / kDecWarps);
-    k_decode<<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err);
+    k_decode<<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u);
 }
 
 }  // namespace flic
