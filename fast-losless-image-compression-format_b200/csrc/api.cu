@@ -173,6 +173,7 @@ static int make_geo(const void *base, uint32_t n, uint32_t w, uint32_t h, uint32
     g->pitch = (uint64_t)w * c;
     g->img_stride = g->pitch * h;
     g->aligned16 = (((uintptr_t)base | g->pitch | g->img_stride) & 15u) == 0;
+    g->aligned32 = (((uintptr_t)base | g->pitch | g->img_stride) & 31u) == 0;
     if ((uint64_t)n * g->nb >= (1ull << 31)) return FLIC_E_ARG;
     return FLIC_OK;
 }

@@ -18,7 +18,7 @@ constexpr int kL = FLIC_MAX_CODE_LEN;        // max code length
 constexpr int kLutSize = 1 << kL;
 constexpr int kHdrWords = 8;                 // 32-byte stream header
 constexpr int kBlkHdrWords = 32 + kBH / 2;   // 256 length nibbles + 32 u16 row word counts
-constexpr int kRowWordsMax = (kBW * 4 * kL + 31) / 32;  // 176: worst-case words of one row sub-stream
+constexpr int kRowWordsMax = (kBW * 4 * kL + 31) / 32;  // 160: worst-case words of one row sub-stream
 constexpr uint32_t kMagic = 0x30504C46u;
 constexpr uint32_t kLenSole = 15;
 
@@ -32,6 +32,7 @@ struct Geo {
     uint32_t nbx, nby, nb;       // blocks per image (x, y, total)
     uint64_t pitch, img_stride;  // bytes
     uint32_t aligned16;          // base, pitch and image stride are all 16-byte multiples
+    uint32_t aligned32;          // ... and 32-byte multiples (256-bit stores in k_decode)
 };
 
 struct BlockPos {

@@ -315,7 +315,7 @@ __device__ __forceinline__ void decode_chunk(BitReader &br, const RowStream &rs,
 
 template <int C, bool SG>
 __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel, uint32_t m2048, uint8_t *dst, int bwa,
-                            bool active, bool aligned, int lane) {
+                            bool active, int aligned, int lane) {
     constexpr int U = Chunk<C>::U, W = Chunk<C>::W;
     const uint32_t amask = __ballot_sync(0xFFFFFFFFu, active);
     BitReader br;
@@ -355,7 +355,11 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
         else
             decode_chunk<C, SG, false>(br, rs, acc, luts, wsel, m2048, o);
         uint8_t *d = dst + (size_t)x * C;
-        if (aligned) {
+        if (W == 8 && aligned == 2) {  // one 256-bit store: a whole 32-byte sector per lane and half the LSU wavefronts
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                         "r"(o[3]), "r"(o[4 % W]), "r"(o[5 % W]), "r"(o[6 % W]), "r"(o[7 % W])
+                         : "memory");
+        } else if (aligned) {
 #pragma unroll
             for (int i = 0; i < W; i += 4)
                 *reinterpret_cast<uint4 *>(d + 4 * i) = make_uint4(o[i], o[i + 1], o[i + 2], o[i + 3]);
@@ -426,7 +430,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
     uint8_t *dst = pixels + (uint64_t)p.img * g.img_stride + (uint64_t)(p.y0 + lane) * g.pitch +
                    (uint64_t)p.x0 * g.c;
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) != 0 && g.c >= 3;
-    const bool aligned = g.aligned16 != 0;
+    const int aligned = g.aligned16 ? (g.aligned32 ? 2 : 1) : 0;  // 0: byte stores, 1: 16-byte, 2: 32-byte
     const char *lb = reinterpret_cast<const char *>(&luts[0][0]);
     const uint32_t wsel = (uint32_t)warp << 11;
     static_assert(kLutSize * 2 == 2048, "wsel assumes 2 KB per warp LUT");

@@ -400,35 +400,48 @@ struct Lookback {
     }
 };
 
-constexpr int kStagePitch = kRowWordsMax + 1;  // odd pitch: the interleaving copy-out reads a column conflict-free
+// Staging tile: per row 3 pad words (they absorb the all-zero upper words of a code group placed at
+// the very start of a row) + kRowWordsMax data words; the pitch is odd, so the interleaving copy-out
+// reads a column conflict-free.
+constexpr int kStagePad = 3;
+constexpr int kStagePitch = kStagePad + kRowWordsMax + ((kStagePad + kRowWordsMax) % 2 == 0 ? 1 : 0);
+static_assert(kBH * kStagePitch % 4 == 0, "zero-fill uses 16-byte stores");
 
-// byte j of w, times eight (a uint2 table offset)
-__device__ __forceinline__ uint32_t byte_x8(uint32_t w, int j) {
-    return j == 0 ? (w << 3) & 0x7F8u : (w >> (8 * j - 3)) & 0x7F8u;
+__device__ __forceinline__ void red_or_shared(uint32_t addr, int off, uint32_t v) {
+    if (off == -4) asm volatile("red.shared.or.b32 [%0+-4], %1;" ::"r"(addr), "r"(v) : "memory");
+    else if (off == -8) asm volatile("red.shared.or.b32 [%0+-8], %1;" ::"r"(addr), "r"(v) : "memory");
+    else asm volatile("red.shared.or.b32 [%0+-12], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// Looks up the lane's 4*C symbols and merges them pairwise on the FMA pipe: a table entry is
-// {code, len << 16 | 2^len}, so (code0 << len1) | code1 is one IMAD.  pc[i] = code bits of
-// symbols 2i,2i+1 (at most 22), pl[i] = their bit count.  Returns the lane's total bit count.
-template <int C, bool kFull>
-__device__ __forceinline__ uint32_t gather_pairs(const uint32_t (&w)[C], int nv, const uint2 *tab, uint32_t (&pc)[2 * C],
-                                                 uint32_t (&pl)[2 * C]) {
+// Opaque multipliers (kernel arguments): x >> k is issued as IMAD.HI(x, 2^(32-k)) on the FMA pipe instead
+// of SHF on the ALU pipe, which is the one this kernel saturates.
+struct PackMul { uint32_t m8, m10, m18, m26; };  // 2^8 (>>24), 2^10 (>>22), 2^18 (>>14), 2^26 (>>6)
+
+// The code group ("quad") of the four symbols in word w, MSB-first: value in qhi:qlo (at most 40 bits,
+// right-aligned), bit count returned.  A table entry is code | len << 24; the pair merge
+// ((e0 << len1) | e1) & 0xFFFFF leaves the length fields above bit 24 where they are masked off, and the
+// sum of entries carries the sum of lengths in its top byte (the code fields cannot carry into it).
+template <bool kFull>
+__device__ __forceinline__ uint32_t quad_of(uint32_t w, int first, int nv, const uint32_t *tab, const PackMul &pm,
+                                            uint32_t &qlo, uint32_t &qhi) {
     const char *t = reinterpret_cast<const char *>(tab);
-    uint32_t xs = 0;
-#pragma unroll
-    for (int j = 0; j < 4 * C; j += 2) {
-        uint2 e0 = *reinterpret_cast<const uint2 *>(t + byte_x8(w[j >> 2], j & 3));
-        uint2 e1 = *reinterpret_cast<const uint2 *>(t + byte_x8(w[j >> 2], (j & 3) + 1));
-        if (!kFull) {
-            if (j >= nv) e0 = make_uint2(0u, 1u);
-            if (j + 1 >= nv) e1 = make_uint2(0u, 1u);
-        }
-        pc[j >> 1] = e0.x * (e1.y & 0xFFFFu) + e1.x;
-        const uint32_t x = e0.y + e1.y;  // high half: len0 + len1 (the low halves cannot carry into it)
-        pl[j >> 1] = x >> 16;
-        xs += x;
+    uint32_t e0 = *reinterpret_cast<const uint32_t *>(t + ((w << 2) & 0x3FCu));
+    uint32_t e1 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m26) & 0x3FCu));
+    uint32_t e2 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m18) & 0x3FCu));
+    uint32_t e3 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m10) & 0x3FCu));
+    if (!kFull) {  // ragged right edge: symbols at or past nv contribute nothing
+        if (first + 0 >= nv) e0 = 0;
+        if (first + 1 >= nv) e1 = 0;
+        if (first + 2 >= nv) e2 = 0;
+        if (first + 3 >= nv) e3 = 0;
     }
-    return xs >> 16;
+    const uint32_t pa = ((e0 << __umulhi(e1, pm.m8)) | e1) & 0xFFFFFu;
+    const uint32_t pb = ((e2 << __umulhi(e3, pm.m8)) | e3) & 0xFFFFFu;
+    const uint32_t sb = e2 + e3;
+    const uint32_t lb = __umulhi(sb, pm.m8);
+    qlo = (pa << lb) | pb;
+    qhi = __funnelshift_l(pa, 0u, lb);
+    return __umulhi(e0 + e1 + sb, pm.m8);
 }
 
 template <int C>
@@ -436,9 +449,9 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
                                                       const uint16_t *__restrict__ table,
                                                       uint32_t *__restrict__ streams, uint64_t capacity_words,
                                                       unsigned long long *status, unsigned long long *dirE,
-                                                      uint32_t *err) {
+                                                      uint32_t *err, PackMul pm) {
     __shared__ __align__(16) uint32_t stage[kBH * kStagePitch];
-    __shared__ uint2 tab[256];  // {code, len << 16 | 2^len}; len 0 for a sole symbol
+    __shared__ uint32_t tab[256];  // code | len << 24; 0 for a sole symbol (no bits)
     __shared__ uint8_t nib[256];
     __shared__ uint32_t rwc[kBH], rowoff[kBH];
     __shared__ unsigned long long s_gb, s_base;
@@ -460,57 +473,59 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     {
         uint32_t e = table[gb * 256 + tid], l = e >> 12;
         nib[tid] = (uint8_t)l;
-        if (l == kLenSole) l = 0;
-        tab[tid] = make_uint2(l ? (e & 0xFFFu) : 0u, (l << 16) | (1u << l));
+        tab[tid] = (l == kLenSole || l == 0) ? 0u : ((e & 0xFFFu) | (l << 24));
     }
-    uint32_t res[kBH / kEncWarps][C];
-    int nv[kBH / kEncWarps];
-#pragma unroll
-    for (int q = 0; q < kBH / kEncWarps; ++q) {
-        const int r = warp + kEncWarps * q;
-        nv[q] = r < (int)p.bha ? C * max(0, min(4, (int)p.bwa - 4 * lane)) : 0;
+    // residual words of the lane's four pixels in row r (k_histograms wrote them in this lane order)
+    auto load_row = [&](int r, uint32_t(&v)[C]) {
         const uint32_t *t = resid + ((gb * kBH + r) * 32 + lane) * C;
         if (C == 4) {
-            uint4 v = ldg_nc_v4(t);
-            res[q][0] = v.x; res[q][1 % C] = v.y; res[q][2 % C] = v.z; res[q][3 % C] = v.w;
+            uint4 x = ldg_nc_v4(t);
+            v[0] = x.x; v[1 % C] = x.y; v[2 % C] = x.z; v[3 % C] = x.w;
         } else if (C == 2) {
-            uint2 v = __ldg(reinterpret_cast<const uint2 *>(t));
-            res[q][0] = v.x; res[q][1 % C] = v.y;
+            uint2 x = __ldg(reinterpret_cast<const uint2 *>(t));
+            v[0] = x.x; v[1 % C] = x.y;
         } else {
 #pragma unroll
-            for (int j = 0; j < C; ++j) res[q][j] = __ldg(t + j);
+            for (int j = 0; j < C; ++j) v[j] = __ldg(t + j);
         }
-    }
+    };
+    const int nvfull = C * max(0, min(4, (int)p.bwa - 4 * lane));
+    uint32_t nxt[C];
+    load_row(warp, nxt);
     __syncthreads();
 
-    // FLP0 §5: one warp per row.  Each lane merges its 4*C codes pairwise, a warp scan of bit counts
-    // places them, and 32-bit words are OR-ed into the zeroed staging row.
+    // FLP0 §5: one warp per row.  Each lane turns its 4*C symbols into C code groups, a warp scan of bit
+    // counts places them, and every group is OR-ed straight into the zeroed staging row at its END bit
+    // position: group << ((32 - end) & 31) occupies the word the group ends in and the one or two before.
+    const uint32_t sstage = (uint32_t)__cvta_generic_to_shared(stage);
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
         const int r = warp + kEncWarps * q;
-        uint32_t pc[2 * C], pl[2 * C], nbits;
-        if (nv[q] == 4 * C) nbits = gather_pairs<C, true>(res[q], 4 * C, tab, pc, pl);
-        else nbits = gather_pairs<C, false>(res[q], nv[q], tab, pc, pl);  // ragged edge / lanes past the row
+        uint32_t cur[C];
+#pragma unroll
+        for (int j = 0; j < C; ++j) cur[j] = nxt[j];
+        if (q + 1 < kBH / kEncWarps) load_row(r + kEncWarps, nxt);  // next row's residuals fly while this one packs
+        const int nv = r < (int)p.bha ? nvfull : 0;
+        uint32_t qlo[C], qhi[C], ql[C], nbits = 0;
+        if (nv == 4 * C) {
+#pragma unroll
+            for (int j = 0; j < C; ++j) { ql[j] = quad_of<true>(cur[j], 4 * j, 4 * C, tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < C; ++j) { ql[j] = quad_of<false>(cur[j], 4 * j, nv, tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+        }
         const uint32_t incl = warp_incl_scan(nbits, lane);
         if (lane == 31) rwc[r] = (incl + 31u) >> 5;
-        const uint32_t o = incl - nbits;
-        // lanes with no bits (past the row end) park on the row's first word and OR zeros into it
-        uint32_t *dst = &stage[r * kStagePitch + (nbits ? (o >> 5) : 0u)];
-        // acc holds the pending (< 32) bits in its low end; older, already emitted bits may linger above
-        // them — every extraction below truncates to the 32 bits it wants, so they are harmless.  The OR is
-        // issued unconditionally (a zero when there is nothing to flush): straight-line code, no branches.
-        uint32_t acc = 0, na = o & 31u;
+        // nb = -(bit address in shared memory of the lane's next free bit); its low 5 bits are the shift
+        uint32_t nb = 0u - (8u * (sstage + 4u * (uint32_t)(r * kStagePitch + kStagePad)) + (incl - nbits));
 #pragma unroll
-        for (int i = 0; i < 2 * C; ++i) {
-            const unsigned long long a64 = ((unsigned long long)acc << pl[i]) | pc[i];
-            na += pl[i];
-            const bool flush = na >= 32u;
-            na -= flush ? 32u : 0u;
-            atomicOr(dst, flush ? (uint32_t)(a64 >> (na & 31u)) : 0u);
-            dst += flush ? 1 : 0;
-            acc = (uint32_t)a64;
+        for (int j = 0; j < C; ++j) {
+            nb -= ql[j];
+            const uint32_t a = ((31u - nb) >> 3) & ~3u;  // byte address one past the word the group ends in
+            red_or_shared(a, -4, __funnelshift_l(0u, qlo[j], nb));
+            red_or_shared(a, -8, __funnelshift_l(qlo[j], qhi[j], nb));
+            if (__any_sync(0xFFFFFFFFu, ql[j] > 32u)) red_or_shared(a, -12, __funnelshift_l(qhi[j], 0u, nb));
         }
-        atomicOr(dst, na ? acc << ((32u - na) & 31u) : 0u);
     }
     __syncthreads();
 
@@ -556,18 +571,18 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     const uint32_t minw = s_minw, bha = p.bha, inter = minw * bha;
     out += kBlkHdrWords;
     if (bha == (uint32_t)kBH) {
-        for (uint32_t i = tid; i < inter; i += kEncThreads) out[i] = stage[(i & 31u) * kStagePitch + (i >> 5)];
+        for (uint32_t i = tid; i < inter; i += kEncThreads) out[i] = stage[(i & 31u) * kStagePitch + kStagePad + (i >> 5)];
     } else {
         for (uint32_t i = tid; i < inter; i += kEncThreads) {
             uint32_t k = i / bha, r = i - k * bha;
-            out[i] = stage[r * kStagePitch + k];
+            out[i] = stage[r * kStagePitch + kStagePad + k];
         }
     }
     // tails, row by row
     for (uint32_t r = warp; r < bha; r += kEncWarps) {
         const uint32_t cnt = rwc[r] - minw;
         uint32_t *o = out + inter + (rowoff[r] - r * minw);
-        const uint32_t *src = &stage[r * kStagePitch + minw];
+        const uint32_t *src = &stage[r * kStagePitch + kStagePad + minw];
         for (uint32_t i = lane; i < cnt; i += 32) o[i] = src[i];
     }
 }
@@ -576,8 +591,9 @@ void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table,
                  uint64_t capacity_words, unsigned long long *d_status, unsigned long long *d_dirE,
                  uint32_t *d_err, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;  // caller has zeroed d_status[0..total] on this stream
+    const PackMul pm = {1u << 8, 1u << 10, 1u << 18, 1u << 26};
 #define FLIC_PACK(C) \
-    k_pack<C><<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_streams, capacity_words, d_status, d_dirE, d_err)
+    k_pack<C><<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_streams, capacity_words, d_status, d_dirE, d_err, pm)
     switch (g.c) {
         case 1: FLIC_PACK(1); break;
         case 2: FLIC_PACK(2); break;
