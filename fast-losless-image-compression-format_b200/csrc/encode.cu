@@ -335,7 +335,7 @@ void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, 
 
 // ---------------------------------------------------------------------- k_pack
 constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValMask = (1ull << 62) - 1;
-constexpr uint32_t kSpinLimit = 1u << 24;
+constexpr uint32_t kSpinLimit = 1u << 22;
 
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
     unsigned long long v;
@@ -368,33 +368,38 @@ struct Lookback {
         done = true;
         if (lane == 0) st_status(status + gb, kFlagPrefix | ((excl + size) & kValMask));
     }
-    // consumes every 32-block window that is fully published; returns when one is not
+    // consumes every 32-block window that is fully published; returns when one is not.  With ~1200 blocks
+    // in flight a look-back walks tens of windows, so a window is kept to a dozen instructions: block
+    // sizes fit 32 bits and are summed by one REDUX; only a found prefix needs its 62-bit value moved.
     __device__ __forceinline__ void poll(int lane) {
         while (!done) {
             const long long my = idx - lane;
             const unsigned long long v = my >= 0 ? ld_status(status + my) : kFlagPrefix;
-            if (__any_sync(0xFFFFFFFFu, (v >> 62) == 0)) return;
-            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
-            unsigned long long val = v & kValMask;
-            if (pm && lane > __ffs(pm) - 1) val = 0;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                uint32_t lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)val, d);
-                uint32_t hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(val >> 32), d);
-                val += ((unsigned long long)hi << 32) | lo;
+            const uint32_t flag = (uint32_t)(v >> 62);
+            if (__any_sync(0xFFFFFFFFu, flag == 0)) return;
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, flag == 2);
+            const int first = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor holding an inclusive prefix
+            excl += __reduce_add_sync(0xFFFFFFFFu, lane < first ? (uint32_t)v : 0u);
+            if (pm) {
+                const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)v, first);
+                const uint32_t hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)((v & kValMask) >> 32), first);
+                excl += ((unsigned long long)hi << 32) | lo;
+                publish(lane);
+            } else {
+                idx -= 32;
             }
-            excl += val;
-            idx -= 32;
-            if (pm || idx < 0) publish(lane);
         }
     }
     __device__ __forceinline__ void finish(int lane, uint32_t *err) {
         uint32_t spins = 0;
         while (!done) {
             poll(lane);
-            if (!done && ++spins >= kSpinLimit) {
-                if (lane == 0) atomicOr(err, kErrWatchdog);
-                publish(lane);
+            if (!done) {
+                __nanosleep(64);  // a predecessor is still packing: do not burn issue slots other CTAs can use
+                if (++spins >= kSpinLimit) {
+                    if (lane == 0) atomicOr(err, kErrWatchdog);
+                    publish(lane);
+                }
             }
         }
     }
@@ -570,20 +575,25 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     // interleaved region: word k of row r lands at k*bha + r (coalesced stores, conflict-free column reads)
     const uint32_t minw = s_minw, bha = p.bha, inter = minw * bha;
     out += kBlkHdrWords;
-    if (bha == (uint32_t)kBH) {
-        for (uint32_t i = tid; i < inter; i += kEncThreads) out[i] = stage[(i & 31u) * kStagePitch + kStagePad + (i >> 5)];
+    if (bha == (uint32_t)kBH) {  // thread = (k = warp, r = lane): i = k*32 + r = tid, then k += 8 per step
+        const uint32_t *src = stage + lane * kStagePitch + kStagePad + warp;
+        uint32_t *dst = out + tid;
+        for (uint32_t k = warp; k < minw; k += kEncWarps, src += kEncWarps, dst += kEncThreads) *dst = *src;
     } else {
         for (uint32_t i = tid; i < inter; i += kEncThreads) {
             uint32_t k = i / bha, r = i - k * bha;
             out[i] = stage[r * kStagePitch + kStagePad + k];
         }
     }
-    // tails, row by row
-    for (uint32_t r = warp; r < bha; r += kEncWarps) {
-        const uint32_t cnt = rwc[r] - minw;
-        uint32_t *o = out + inter + (rowoff[r] - r * minw);
-        const uint32_t *src = &stage[r * kStagePitch + kStagePad + minw];
-        for (uint32_t i = lane; i < cnt; i += 32) o[i] = src[i];
+    // tails (a few words per row, back to back in row order): eight threads per row
+    {
+        const uint32_t r = tid >> 3, j = tid & 7;
+        if (r < bha) {
+            const uint32_t cnt = rwc[r] - minw;
+            uint32_t *o = out + inter + (rowoff[r] - r * minw);
+            const uint32_t *src = &stage[r * kStagePitch + kStagePad + minw];
+            for (uint32_t i = j; i < cnt; i += 8) o[i] = src[i];
+        }
     }
 }
 
