@@ -60,7 +60,7 @@ def load_library():
         "flic_decode_batch": (i32, [vp, vp, vp, u32, vp, u64]),
         "flic_peek": (i32, [vp, u64, C.POINTER(_Info)]),
         "flic_splice_block_rows": (i32, [C.POINTER(vp), C.POINTER(u64), u32, vp, u64, C.POINTER(u64)]),
-        "flic_stage_histograms": (i32, [vp, vp, u32, u32, u32, u32, u32, vp, vp]),
+        "flic_stage_histograms": (i32, [vp, vp, u32, u32, u32, u32, u32, vp, vp, vp]),
         "flic_stage_tables": (i32, [vp, vp, u64, vp, vp]),
         "flic_launch_count": (u64, [vp]),
         "flic_set_kernel_timing": (i32, [vp, i32]),
@@ -209,10 +209,10 @@ class Codec:
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNELS)}
 
     # ---- stage-level (parity tests) ----
-    def stage_histograms(self, pixels, hist, flags=PRED_LEFT, stream=0):
+    def stage_histograms(self, pixels, hist, flags=PRED_LEFT, stream=0, flat=None):
         n, h, w, c = pixels.shape
         self._chk(self.lib.flic_stage_histograms(self.h, _ptr(pixels), n, w, h, c, flags, _ptr(hist),
-                                                 C.c_void_p(stream)))
+                                                 _ptr(flat) if flat is not None else None, C.c_void_p(stream)))
 
     def stage_tables(self, hist, table, stream=0):
         self._chk(self.lib.flic_stage_tables(self.h, _ptr(hist), hist.shape[0], _ptr(table), C.c_void_p(stream)))

@@ -20,6 +20,7 @@ struct flic_ctx {
     uint64_t ws_blocks = 0;
     uint16_t *d_hist = nullptr, *d_table = nullptr;
     uint32_t *d_resid = nullptr;  // residual plane: 32 rows x 32 lanes x C words (<= 16 KB) per block
+    uint2 *d_flat = nullptr;      // per block {flat-channel mask, values}
     unsigned long long *d_status = nullptr, *d_dirE = nullptr;
     uint32_t *d_err = nullptr;
     uint32_t *h_err = nullptr;  // pinned
@@ -70,7 +71,7 @@ static int cuda_fail(flic_ctx *ctx, cudaError_t e, const char *what) {
 
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
-extern "C" int flic_version(void) { return 2; }
+extern "C" int flic_version(void) { return (int)kVersion; }
 
 extern "C" const char *flic_strerror(int code) {
     switch (code) {
@@ -133,7 +134,7 @@ extern "C" void flic_destroy(flic_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_status); cudaFree(ctx->d_dirE);
-    cudaFree(ctx->d_resid); cudaFree(ctx->d_err);
+    cudaFree(ctx->d_resid); cudaFree(ctx->d_flat); cudaFree(ctx->d_err);
     for (int i = 0; i < 2; ++i) {
         cudaFree(ctx->d_pix[i]); cudaFree(ctx->d_str[i]); cudaFree(ctx->d_off[i]);
         if (ctx->h_off[i]) cudaFreeHost(ctx->h_off[i]);
@@ -153,10 +154,11 @@ extern "C" void flic_destroy(flic_ctx *ctx) {
 static int ensure_workspace(flic_ctx *ctx, uint64_t blocks) {
     if (blocks <= ctx->ws_blocks) return FLIC_OK;
     cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_status); cudaFree(ctx->d_dirE);
-    cudaFree(ctx->d_resid);
-    ctx->d_hist = ctx->d_table = nullptr; ctx->d_status = ctx->d_dirE = nullptr; ctx->d_resid = nullptr;
+    cudaFree(ctx->d_resid); cudaFree(ctx->d_flat);
+    ctx->d_hist = ctx->d_table = nullptr; ctx->d_status = ctx->d_dirE = nullptr; ctx->d_resid = nullptr; ctx->d_flat = nullptr;
     ctx->ws_blocks = 0;
     CU(cudaMalloc(&ctx->d_resid, blocks * (uint64_t)kBH * 512));
+    CU(cudaMalloc(&ctx->d_flat, blocks * sizeof(uint2)));
     CU(cudaMalloc(&ctx->d_hist, blocks * 256 * sizeof(uint16_t)));
     CU(cudaMalloc(&ctx->d_table, blocks * 256 * sizeof(uint16_t)));
     CU(cudaMalloc(&ctx->d_status, (blocks + 1) * sizeof(unsigned long long)));
@@ -179,13 +181,13 @@ static int make_geo(const void *base, uint32_t n, uint32_t w, uint32_t h, uint32
 }
 
 extern "C" int flic_stage_histograms(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t n, uint32_t w, uint32_t h,
-                                     uint32_t c, uint32_t flags, uint16_t *d_hist, void *stream) {
+                                     uint32_t c, uint32_t flags, uint16_t *d_hist, uint32_t *d_flat, void *stream) {
     if (!ctx || !d_pixels || !d_hist) return FLIC_E_ARG;
     Geo g;
     int rc = make_geo(d_pixels, n, w, h, c, flags, &g);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
-    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, (cudaStream_t)stream); launch_histograms(d_pixels, g, d_hist, nullptr, (cudaStream_t)stream); }
+    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, (cudaStream_t)stream); launch_histograms(d_pixels, g, d_hist, nullptr, reinterpret_cast<uint2 *>(d_flat), (cudaStream_t)stream); }
     ctx->launches += 1;
     CU(cudaGetLastError());
     return FLIC_OK;
@@ -214,11 +216,11 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const uint64_t cap_words = capacity_bytes / 4;
-    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s); launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, s); }
+    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s); launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, ctx->d_flat, s); }
     { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, (uint64_t)n * g.nb, ctx->d_table, s); }
     CU(cudaMemsetAsync(ctx->d_status, 0, ((uint64_t)n * g.nb + 1) * sizeof(unsigned long long), s));
     { KernelTimer t(ctx, FLIC_K_PACK, s);
-      launch_pack(ctx->d_resid, g, ctx->d_table, (uint32_t *)d_streams, cap_words, ctx->d_status, ctx->d_dirE, ctx->d_err, s); }
+      launch_pack(ctx->d_resid, g, ctx->d_table, ctx->d_flat, (uint32_t *)d_streams, cap_words, ctx->d_status, ctx->d_dirE, ctx->d_err, s); }
     { KernelTimer t(ctx, FLIC_K_FINALIZE, s);
       launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s); }
     ctx->launches += 4;
@@ -383,7 +385,7 @@ extern "C" int flic_peek(const uint8_t *s, uint64_t size, flic_image_info *info)
     if (!s || !info || size < FLIC_HEADER_BYTES) return FLIC_E_FORMAT;
     uint32_t wd[8];
     memcpy(wd, s, sizeof wd);
-    if (wd[0] != kMagic || (wd[1] & 0xFFFFu) != 2u || wd[7] != (uint32_t)kL) return FLIC_E_FORMAT;
+    if (wd[0] != kMagic || (wd[1] & 0xFFFFu) != kVersion || wd[7] != (uint32_t)kL) return FLIC_E_FORMAT;
     info->channels = (wd[1] >> 16) & 0xFFu;
     info->flags = wd[1] >> 24;
     info->width = wd[2];
@@ -473,7 +475,7 @@ extern "C" int flic_splice_block_rows(const uint8_t *const *parts, const uint64_
     if (nb >= (1ull << 32) || pw >= (1ull << 32) || height >= (1ull << 32)) return FLIC_E_ARG;
     const uint64_t total = 4ull * (kHdrWords + nb + 1 + pw);
     if (total > out_capacity) return FLIC_E_CAPACITY;
-    uint32_t hdr[8] = {kMagic, 2u | (first.channels << 16) | (first.flags << 24), first.width, (uint32_t)height,
+    uint32_t hdr[8] = {kMagic, kVersion | (first.channels << 16) | (first.flags << 24), first.width, (uint32_t)height,
                        first.block_w | (first.block_h << 16), (uint32_t)nb, (uint32_t)pw, (uint32_t)kL};
     memcpy(out, hdr, sizeof hdr);
     uint8_t *dir = out + 4 * kHdrWords, *payload = dir + 4 * (nb + 1);

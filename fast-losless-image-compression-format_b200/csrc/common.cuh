@@ -17,7 +17,9 @@ constexpr int kBH = FLIC_BLOCK_H;            // rows per block == lanes per deco
 constexpr int kL = FLIC_MAX_CODE_LEN;        // max code length
 constexpr int kLutSize = 1 << kL;
 constexpr int kHdrWords = 8;                 // 32-byte stream header
-constexpr int kBlkHdrWords = 32 + kBH / 2;   // 256 length nibbles + 32 u16 row word counts
+constexpr int kFlatWord = 32 + kBH / 2;     // block header word holding the flat-channel mask; the values follow
+constexpr int kBlkHdrWords = kFlatWord + 2;  // 256 length nibbles + 32 u16 row word counts + flat mask + flat values
+constexpr uint32_t kVersion = 3;
 constexpr int kRowWordsMax = (kBW * 4 * kL + 31) / 32;  // 160: worst-case words of one row sub-stream
 constexpr uint32_t kMagic = 0x30504C46u;
 constexpr uint32_t kLenSole = 15;
@@ -163,9 +165,10 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 // launchers (defined in the .cu files, used by api.cu)
-void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, cudaStream_t s);
+void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, uint2 *d_flat,
+                       cudaStream_t s);
 void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, cudaStream_t s);
-void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, uint32_t *d_streams,
+void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, const uint2 *d_flat, uint32_t *d_streams,
                  uint64_t capacity_words, unsigned long long *d_status, unsigned long long *d_dirE,
                  uint32_t *d_err, cudaStream_t s);
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,

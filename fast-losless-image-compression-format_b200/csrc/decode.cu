@@ -284,18 +284,21 @@ __device__ __forceinline__ void store_bytes(uint8_t *dst, uint32_t px) {
     for (int ch = 0; ch < C; ++ch) dst[ch] = (uint8_t)(px >> (8 * ch));
 }
 
-// U pixels per chunk fill whole 16-byte stores (two for RGBA: a full 32-byte sector)
-template <int C> struct Chunk {
+// U pixels per chunk fill whole 16-byte stores (two for RGBA: a full 32-byte sector).
+// FM: compile-time mask of flat channels (FLP0 §2b) — they carry no symbols; CS = symbols per pixel.
+template <int C, int FM> struct Chunk {
     static constexpr int U = (C == 4) ? 8 : (C == 2 ? 8 : 16);
-    static constexpr int W = U * C / 4;                          // words per chunk
-    static constexpr int kMaxRefills = (U * C * kL + 31) / 32 + 1;  // words a chunk can request
+    static constexpr int W = U * C / 4;  // words per chunk
+    static constexpr int CS = C - ((FM & 1) + ((FM >> 1) & 1) + ((FM >> 2) & 1) + ((FM >> 3) & 1));
+    static constexpr int kMaxRefills = (U * CS * kL + 31) / 32 + 1;  // words a chunk can request
 };
 
-// One chunk of U pixels: U*C symbols with a refill check before every kSymsPerRefill-th.
-template <int C, bool SG, bool kFast>
+// One chunk of U pixels: U*CS symbols with a refill check before every kSymsPerRefill-th.
+template <int C, bool SG, int FM, bool kFast>
 __device__ __forceinline__ void decode_chunk(BitReader &br, const RowStream &rs, Acc &acc, const char *luts,
                                              uint32_t wsel, uint32_t m2048, uint32_t *o) {
-    constexpr int U = Chunk<C>::U;
+    constexpr int U = Chunk<C, FM>::U;
+    int sidx = 0;  // compile-time after unrolling
 #pragma unroll
     for (int g = 0; g < U / 4; ++g) {
         uint32_t px[4];
@@ -303,7 +306,9 @@ __device__ __forceinline__ void decode_chunk(BitReader &br, const RowStream &rs,
         for (int u = 0; u < 4; ++u) {
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
-                if (((g * 4 + u) * C + ch) % kSymsPerRefill == 0) refill<kFast>(br, rs);
+                if ((FM >> ch) & 1) continue;
+                if (sidx % kSymsPerRefill == 0) refill<kFast>(br, rs);
+                ++sidx;
                 acc_add<C>(acc, ch, get(br, luts, wsel, m2048));
             }
             px[u] = acc_pixel<C, SG>(acc);
@@ -313,10 +318,20 @@ __device__ __forceinline__ void decode_chunk(BitReader &br, const RowStream &rs,
     acc_clean(acc);
 }
 
-template <int C, bool SG>
+// channel `ch` of the running sums := v (flat channels hold their constant for the whole block)
+__device__ __forceinline__ void acc_set(Acc &v, int ch, uint32_t val) {
+    const uint32_t keep = (ch & 2) ? 0x0000FFFFu : 0xFFFF0000u, put = val << ((ch & 2) ? 24 : 8);
+    if (ch & 1) v.b = (v.b & keep) | put;
+    else v.a = (v.a & keep) | put;
+}
+
+// FM >= 0: the block's flat mask is the compile-time FM (0, or 8 = opaque-alpha RGBA), rows run in unrolled
+// chunks.  FM < 0: any other mask, taken from `fmask` at run time — a plain per-pixel loop (rare blocks).
+template <int C, bool SG, int FM>
 __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel, uint32_t m2048, uint8_t *dst, int bwa,
-                            bool active, int aligned, int lane) {
-    constexpr int U = Chunk<C>::U, W = Chunk<C>::W;
+                            bool active, int aligned, int lane, uint32_t fmask, uint32_t fvals) {
+    constexpr int FMC = FM < 0 ? 0 : FM;
+    constexpr int U = Chunk<C, FMC>::U, W = Chunk<C, FMC>::W;
     const uint32_t amask = __ballot_sync(0xFFFFFFFFu, active);
     BitReader br;
     reader_init(br, rs);
@@ -327,9 +342,12 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
     if (active) {
         BitReader t = br;
         Acc z = {0u, 0u};
+        int sidx = 0;
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            if (ch % kSymsPerRefill == 0) refill<false>(t, rs);
+            if ((fmask >> ch) & 1u) continue;
+            if (sidx % kSymsPerRefill == 0) refill<false>(t, rs);
+            ++sidx;
             acc_add<C>(z, ch, get(t, luts, wsel, m2048));
         }
         first = __byte_perm(z.a, z.b, 0x7351);
@@ -345,34 +363,40 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
     if (lane == 0) above = 0;
     if (!active) return;
     Acc acc = acc_from<C>(above);
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch)
+        if ((fmask >> ch) & 1u) acc_set(acc, ch, (fvals >> (8 * ch)) & 0xFFu);
 
     int x = 0;
-    for (; x + U <= bwa; x += U) {
-        uint32_t o[W];
-        // fast path while no lane of the warp can leave the interleaved region inside this chunk
-        if (__all_sync(amask, br.k + (uint32_t)Chunk<C>::kMaxRefills <= rs.minw))
-            decode_chunk<C, SG, true>(br, rs, acc, luts, wsel, m2048, o);
-        else
-            decode_chunk<C, SG, false>(br, rs, acc, luts, wsel, m2048, o);
-        uint8_t *d = dst + (size_t)x * C;
-        if (W == 8 && aligned == 2) {  // one 256-bit store: a whole 32-byte sector per lane and half the LSU wavefronts
-            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]),
-                         "r"(o[3]), "r"(o[4 % W]), "r"(o[5 % W]), "r"(o[6 % W]), "r"(o[7 % W])
-                         : "memory");
-        } else if (aligned) {
+    if (FM >= 0) {
+        for (; x + U <= bwa; x += U) {
+            uint32_t o[W];
+            // fast path while no lane of the warp can leave the interleaved region inside this chunk
+            if (__all_sync(amask, br.k + (uint32_t)Chunk<C, FMC>::kMaxRefills <= rs.minw))
+                decode_chunk<C, SG, FMC, true>(br, rs, acc, luts, wsel, m2048, o);
+            else
+                decode_chunk<C, SG, FMC, false>(br, rs, acc, luts, wsel, m2048, o);
+            uint8_t *d = dst + (size_t)x * C;
+            if (W == 8 && aligned == 2) {  // one 256-bit store: a whole 32-byte sector per lane and half the LSU wavefronts
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                             "r"(o[3]), "r"(o[4 % W]), "r"(o[5 % W]), "r"(o[6 % W]), "r"(o[7 % W])
+                             : "memory");
+            } else if (aligned) {
 #pragma unroll
-            for (int i = 0; i < W; i += 4)
-                *reinterpret_cast<uint4 *>(d + 4 * i) = make_uint4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-        } else {
+                for (int i = 0; i < W; i += 4)
+                    *reinterpret_cast<uint4 *>(d + 4 * i) = make_uint4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < W * 4; ++i) d[i] = (uint8_t)(o[i >> 2] >> (8 * (i & 3)));
+                for (int i = 0; i < W * 4; ++i) d[i] = (uint8_t)(o[i >> 2] >> (8 * (i & 3)));
+            }
         }
     }
-    // ragged right edge of the image
+    // ragged right edge of the image, and whole rows of blocks with an uncommon flat mask
     for (; x < bwa; ++x) {
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            if (ch % kSymsPerRefill == 0) refill<false>(br, rs);
+            if ((fmask >> ch) & 1u) continue;  // warp-uniform
+            refill<false>(br, rs);
             acc_add<C>(acc, ch, get(br, luts, wsel, m2048));
         }
         store_bytes<C>(dst + (size_t)x * C, acc_pixel<C, SG>(acc));
@@ -400,7 +424,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
         pw = sw[6];
         off = sw[kHdrWords + p.b];
         end = sw[kHdrWords + p.b + 1];
-        ok = sw[0] == kMagic && (sw[1] & 0xFFFFu) == 2u && sw[2] == g.w && sw[3] == g.h && sw[5] == g.nb && fixed + pw <= swords &&
+        ok = sw[0] == kMagic && (sw[1] & 0xFFFFu) == kVersion && sw[2] == g.w && sw[3] == g.h && sw[5] == g.nb && fixed + pw <= swords &&
              off <= end && end <= pw && end - off >= (uint32_t)kBlkHdrWords;
     }
     if (!ok) {
@@ -418,7 +442,8 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
     uint32_t minw = active ? rc : 0xFFFFFFFFu;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) minw = min(minw, __shfl_xor_sync(0xFFFFFFFFu, minw, d));
-    ok = ok && (uint32_t)kBlkHdrWords + total <= end - off && !__any_sync(0xFFFFFFFFu, !active && rc != 0);
+    const uint32_t fmask = __ldg(blk + kFlatWord), fvals = __ldg(blk + kFlatWord + 1);  // FLP0 §2b
+    ok = ok && (uint32_t)kBlkHdrWords + total <= end - off && !__any_sync(0xFFFFFFFFu, !active && rc != 0) && (fmask >> g.c) == 0;
     if (!ok) {
         if (lane == 0) atomicOr(err, kErrFormat);
         return;
@@ -434,18 +459,25 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
     const char *lb = reinterpret_cast<const char *>(&luts[0][0]);
     const uint32_t wsel = (uint32_t)warp << 11;
     static_assert(kLutSize * 2 == 2048, "wsel assumes 2 KB per warp LUT");
-    switch (g.c) {
-        case 1: decode_rows<1, false>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane); break;
-        case 2: decode_rows<2, false>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane); break;
-        case 3:
-            if (sg) decode_rows<3, true>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane);
-            else decode_rows<3, false>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane);
-            break;
-        default:
-            if (sg) decode_rows<4, true>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane);
-            else decode_rows<4, false>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane);
-            break;
+#define FLIC_ROWS(C, SG, FM) decode_rows<C, SG, FM>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane, fmask, fvals)
+    if (fmask == 0) {
+        switch (g.c) {
+            case 1: FLIC_ROWS(1, false, 0); break;
+            case 2: FLIC_ROWS(2, false, 0); break;
+            case 3: if (sg) FLIC_ROWS(3, true, 0); else FLIC_ROWS(3, false, 0); break;
+            default: if (sg) FLIC_ROWS(4, true, 0); else FLIC_ROWS(4, false, 0); break;
+        }
+    } else if (g.c == 4 && fmask == 8u) {  // opaque (or otherwise constant) alpha: three symbols per pixel
+        if (sg) FLIC_ROWS(4, true, 8); else FLIC_ROWS(4, false, 8);
+    } else {
+        switch (g.c) {
+            case 1: FLIC_ROWS(1, false, -1); break;
+            case 2: FLIC_ROWS(2, false, -1); break;
+            case 3: if (sg) FLIC_ROWS(3, true, -1); else FLIC_ROWS(3, false, -1); break;
+            default: if (sg) FLIC_ROWS(4, true, -1); else FLIC_ROWS(4, false, -1); break;
+        }
     }
+#undef FLIC_ROWS
 }
 
 void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offsets, const Geo &g,

@@ -31,20 +31,39 @@ constexpr int kEncWarps = kEncThreads / 32;
 // resid (optional): the "residual plane" — per block a tile [32 rows][32 lanes][C words] of residual
 // bytes in the lane order above — so that k_pack does not recompute prediction (the kernels are
 // ALU-bound, HBM has headroom: one extra N-byte write buys ~20 % of k_pack's instructions).
+// Per word j of a lane's C words: which of its four bytes belong to a channel named in `mask`
+// (byte b of word j carries channel (4j + b) mod C).
+template <int C>
+__device__ __forceinline__ uint32_t word_channel_bits(uint32_t mask, int j) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) r |= ((mask >> ((4 * j + b) % C)) & 1u) << b;
+    return r;
+}
+
+// flat (optional): per block {mask of flat channels, their values} (FLP0 §2b).  A channel is flat when all
+// its residuals are zero except the block's first pixel's, i.e. the OR of the others is zero; the histogram
+// then leaves the channel out (bwa*bha - 1 zeros and the first pixel's value are taken back off).
 template <int C, bool SG>
 __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__restrict__ pixels, Geo g,
-                                                            uint16_t *__restrict__ hist, uint32_t *__restrict__ resid) {
+                                                            uint16_t *__restrict__ hist, uint32_t *__restrict__ resid,
+                                                            uint2 *__restrict__ flat) {
     __shared__ uint32_t sh[kEncWarps][256];
+    __shared__ uint32_t s_or[C], s_first;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t gb = blockIdx.x;
     const BlockPos p = block_pos(g, gb);
 
     for (int i = tid; i < kEncWarps * 256; i += kEncThreads) (&sh[0][0])[i] = 0;
+    if (tid < C) s_or[tid] = 0;
 
     uint32_t res[kBH / kEncWarps][C];
+    uint32_t orw[C];
     int nv[kBH / kEncWarps];
     const bool fast = g.aligned16 != 0;
     const uint8_t *row = pixels + (uint64_t)p.img * g.img_stride + (uint64_t)(p.y0 + warp) * g.pitch + (uint64_t)p.x0 * C;
+#pragma unroll
+    for (int j = 0; j < C; ++j) orw[j] = 0;
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
         const int r = warp + kEncWarps * q;
@@ -56,6 +75,16 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
             load_lane_pixels<C>(row, lane, (int)p.bwa, fast, v, &nv[q]);
             const uint32_t up = (lane == 0 && r > 0) ? up_pixel<C, SG>(row, g.pitch) : 0u;
             lane_residuals<C, SG>(v, up, lane, res[q]);
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                uint32_t x = res[q][j];
+                if (q == 0 && j == 0 && tid == 0) {  // the block's first pixel: its residual is its value
+                    constexpr uint32_t fm = C == 4 ? 0xFFFFFFFFu : ((1u << (8 * (C & 3))) - 1u);
+                    s_first = x & fm;
+                    x &= ~fm;
+                }
+                orw[j] |= x;
+            }
         }
         if (resid) {
             uint32_t *t = resid + ((gb * kBH + r) * 32 + lane) * C;
@@ -69,6 +98,24 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
         row += kEncWarps * g.pitch;
     }
     __syncthreads();
+    {   // bytes past the lane's last real pixel hold garbage differences: keep them out of the OR
+        const int nvl = C * max(0, min(4, (int)p.bwa - 4 * lane));
+        constexpr int NA = C == 4 ? 1 : C;  // RGBA: byte b is channel b in every word, one accumulator does
+        uint32_t acc[NA];
+#pragma unroll
+        for (int j = 0; j < NA; ++j) acc[j] = 0;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const int nb = min(4, max(0, nvl - 4 * j));
+            const uint32_t vm = nb == 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+            acc[C == 4 ? 0 : j] |= orw[j] & vm;
+        }
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const uint32_t o = __reduce_or_sync(0xFFFFFFFFu, acc[j]);
+            if (lane == 0 && o) atomicOr(&s_or[j], o);
+        }
+    }
     char *my = reinterpret_cast<char *>(sh[warp]);
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
@@ -85,14 +132,32 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < kEncWarps; ++k) s += sh[k][tid];
+    {   // flat channels (FLP0 §2b): T = per channel byte, the OR of all its residual bytes bar the first pixel's
+        uint32_t T;
+        if (C == 4) T = s_or[0];
+        else if (C == 3) {  // word j byte b carries channel (4j + b) mod 3
+            const uint32_t a = s_or[0], b = s_or[1 % C], c = s_or[2 % C];
+            T = (a | __byte_perm(b, 0u, 0x4102) | __byte_perm(c, 0u, 0x4021) | (a >> 24) |
+                 __byte_perm(b, 0u, 0x4434) | __byte_perm(c, 0u, 0x4344)) & 0x00FFFFFFu;
+        } else if (C == 2) { const uint32_t x = s_or[0] | s_or[1 % C]; T = (x | (x >> 16)) & 0xFFFFu; }
+        else { uint32_t x = s_or[0]; x |= x >> 16; T = (x | (x >> 8)) & 0xFFu; }
+        auto nonzero_bytes = [](uint32_t x) { x |= x >> 4; x |= x >> 2; x |= x >> 1; return x & 0x01010101u; };
+        constexpr uint32_t chb = C == 4 ? 0x01010101u : ((1u << (8 * (C & 3))) - 1u) & 0x01010101u;
+        const uint32_t flatb = ~nonzero_bytes(T) & chb;  // bit 8*ch: channel ch is flat
+        const uint32_t first = s_first, npix = p.bwa * p.bha;
+        if (tid == 0) s -= __popc(flatb) * (npix - 1u);   // all those residuals were zeros ...
+        s -= __popc(~nonzero_bytes(first ^ ((uint32_t)tid * 0x01010101u)) & flatb);  // ... bar the first pixel's value
+        if (flat && tid == 0) flat[gb] = make_uint2((flatb * 0x01020408u) >> 24, first & (flatb * 0xFFu));
+    }
     hist[gb * 256 + tid] = (uint16_t)s;
 }
 
-void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, cudaStream_t s) {
+void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, uint2 *d_flat,
+                       cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) && g.c >= 3;
     const unsigned grid = (unsigned)total;
-#define FLIC_HIST(C, SG) k_histograms<C, SG><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid)
+#define FLIC_HIST(C, SG) k_histograms<C, SG><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid, d_flat)
     switch (g.c) {
         case 1: FLIC_HIST(1, false); break;
         case 2: FLIC_HIST(2, false); break;
@@ -426,14 +491,19 @@ struct PackMul { uint32_t m8, m10, m18, m26; };  // 2^8 (>>24), 2^10 (>>22), 2^1
 // right-aligned), bit count returned.  A table entry is code | len << 24; the pair merge
 // ((e0 << len1) | e1) & 0xFFFFF leaves the length fields above bit 24 where they are masked off, and the
 // sum of entries carries the sum of lengths in its top byte (the code fields cannot carry into it).
-template <bool kFull>
-__device__ __forceinline__ uint32_t quad_of(uint32_t w, int first, int nv, const uint32_t *tab, const PackMul &pm,
-                                            uint32_t &qlo, uint32_t &qhi) {
+// Bit b of the skip mask says byte b belongs to a flat channel (FLP0 §2b) and contributes nothing: SK >= 0
+// is that mask at compile time (0, or 8 = the alpha byte of an RGBA word: no table read at all for it),
+// SK < 0 takes it from `skip` at run time.
+template <bool kFull, int SK>
+__device__ __forceinline__ uint32_t quad_of(uint32_t w, int first, int nv, uint32_t skip, const uint32_t *tab,
+                                            const PackMul &pm, uint32_t &qlo, uint32_t &qhi) {
     const char *t = reinterpret_cast<const char *>(tab);
-    uint32_t e0 = *reinterpret_cast<const uint32_t *>(t + ((w << 2) & 0x3FCu));
-    uint32_t e1 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m26) & 0x3FCu));
-    uint32_t e2 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m18) & 0x3FCu));
-    uint32_t e3 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m10) & 0x3FCu));
+    if (SK >= 0) skip = (uint32_t)SK;
+    uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+    if (!(skip & 1u)) e0 = *reinterpret_cast<const uint32_t *>(t + ((w << 2) & 0x3FCu));
+    if (!(skip & 2u)) e1 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m26) & 0x3FCu));
+    if (!(skip & 4u)) e2 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m18) & 0x3FCu));
+    if (!(skip & 8u)) e3 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m10) & 0x3FCu));
     if (!kFull) {  // ragged right edge: symbols at or past nv contribute nothing
         if (first + 0 >= nv) e0 = 0;
         if (first + 1 >= nv) e1 = 0;
@@ -452,6 +522,7 @@ __device__ __forceinline__ uint32_t quad_of(uint32_t w, int first, int nv, const
 template <int C>
 __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restrict__ resid, Geo g,
                                                       const uint16_t *__restrict__ table,
+                                                      const uint2 *__restrict__ flat,
                                                       uint32_t *__restrict__ streams, uint64_t capacity_words,
                                                       unsigned long long *status, unsigned long long *dirE,
                                                       uint32_t *err, PackMul pm) {
@@ -495,6 +566,10 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
         }
     };
     const int nvfull = C * max(0, min(4, (int)p.bwa - 4 * lane));
+    const uint2 fl = flat[gb];  // {mask of flat channels, their values}: CTA-uniform
+    uint32_t skip[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) skip[j] = word_channel_bits<C>(fl.x, j);
     uint32_t nxt[C];
     load_row(warp, nxt);
     __syncthreads();
@@ -512,12 +587,15 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
         if (q + 1 < kBH / kEncWarps) load_row(r + kEncWarps, nxt);  // next row's residuals fly while this one packs
         const int nv = r < (int)p.bha ? nvfull : 0;
         uint32_t qlo[C], qhi[C], ql[C], nbits = 0;
-        if (nv == 4 * C) {
+        if (nv == 4 * C && fl.x == 0) {
 #pragma unroll
-            for (int j = 0; j < C; ++j) { ql[j] = quad_of<true>(cur[j], 4 * j, 4 * C, tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+            for (int j = 0; j < C; ++j) { ql[j] = quad_of<true, 0>(cur[j], 4 * j, 4 * C, 0u, tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+        } else if (nv == 4 * C && C == 4 && fl.x == 8u) {  // opaque-alpha RGBA: three table reads per pixel
+#pragma unroll
+            for (int j = 0; j < C; ++j) { ql[j] = quad_of<true, 8>(cur[j], 4 * j, 4 * C, 8u, tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
         } else {
 #pragma unroll
-            for (int j = 0; j < C; ++j) { ql[j] = quad_of<false>(cur[j], 4 * j, nv, tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+            for (int j = 0; j < C; ++j) { ql[j] = quad_of<false, -1>(cur[j], 4 * j, nv, skip[j], tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
         }
         const uint32_t incl = warp_incl_scan(nbits, lane);
         if (lane == 31) rwc[r] = (incl + 31u) >> 5;
@@ -571,6 +649,8 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
         out[lane] = v;
     } else if (warp == 1 && lane < kBH / 2) {
         out[32 + lane] = rwc[2 * lane] | (rwc[2 * lane + 1] << 16);
+    } else if (warp == 2 && lane < 2) {
+        out[kFlatWord + lane] = lane ? fl.y : fl.x;
     }
     // interleaved region: word k of row r lands at k*bha + r (coalesced stores, conflict-free column reads)
     const uint32_t minw = s_minw, bha = p.bha, inter = minw * bha;
@@ -597,13 +677,13 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     }
 }
 
-void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, uint32_t *d_streams,
+void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, const uint2 *d_flat, uint32_t *d_streams,
                  uint64_t capacity_words, unsigned long long *d_status, unsigned long long *d_dirE,
                  uint32_t *d_err, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;  // caller has zeroed d_status[0..total] on this stream
     const PackMul pm = {1u << 8, 1u << 10, 1u << 18, 1u << 26};
 #define FLIC_PACK(C) \
-    k_pack<C><<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_streams, capacity_words, d_status, d_dirE, d_err, pm)
+    k_pack<C><<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_flat, d_streams, capacity_words, d_status, d_dirE, d_err, pm)
     switch (g.c) {
         case 1: FLIC_PACK(1); break;
         case 2: FLIC_PACK(2); break;
@@ -636,7 +716,7 @@ __global__ void __launch_bounds__(256) k_finalize(Geo g, const unsigned long lon
         } else {
             switch (k) {
                 case 0: v = kMagic; break;
-                case 1: v = 2u | (g.c << 16) | ((g.flags & 0xFFu) << 24); break;
+                case 1: v = kVersion | (g.c << 16) | ((g.flags & 0xFFu) << 24); break;
                 case 2: v = g.w; break;
                 case 3: v = g.h; break;
                 case 4: v = (uint32_t)kBW | ((uint32_t)kBH << 16); break;

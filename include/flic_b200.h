@@ -107,9 +107,11 @@ int flic_splice_block_rows(const uint8_t *const *parts, const uint64_t *part_siz
                            uint8_t *out, uint64_t out_capacity, uint64_t *out_size);
 
 /* ---- stage-level entry points (used by the parity tests) ---------------- */
-/* Per-block residual histograms: d_hist[n_blocks_total][256] u16. */
+/* Per-block residual histograms: d_hist[n_blocks_total][256] u16, flat channels left out;
+ * d_flat (may be NULL): [n_blocks_total][2] u32 = {flat-channel mask, packed flat values}. */
 int flic_stage_histograms(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t n, uint32_t w,
-                          uint32_t h, uint32_t c, uint32_t flags, uint16_t *d_hist, void *stream);
+                          uint32_t h, uint32_t c, uint32_t flags, uint16_t *d_hist,
+                          uint32_t *d_flat, void *stream);
 /* Per-block code tables from histograms: d_table[n_blocks_total][256] u16,
  * entry = len << 12 | code (len 15 = sole symbol). */
 int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t n_blocks_total,

@@ -26,10 +26,33 @@ static inline uint32_t get_u16(const uint8_t *p) { return (uint32_t)p[0] | ((uin
 
 static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
+static inline uint8_t xform(const uint8_t *px, uint32_t c, uint32_t ch, uint32_t flags);
+
 /* per-block payload bound = 32 length words + bh/2 row-count
- * words + bh rows of ceil(bw*c*L/32) words. */
+ * words + 2 flat-channel words + bh rows of ceil(bw*c*L/32) words. */
+#define FLATW 2u
 static size_t block_max_words(uint32_t c, uint32_t bw, uint32_t bh) {
-    return 32u + bh / 2u + (size_t)bh * ceil_div(bw * c * L, 32u);
+    return 32u + bh / 2u + FLATW + (size_t)bh * ceil_div(bw * c * L, 32u);
+}
+
+/* a channel is FLAT in a block when every pixel of the block has the same
+ * (colour-transformed) value in it — e.g. an opaque alpha plane.  Flat channels are named in the
+ * block header with their value and contribute no symbols: not to the histogram, not to the row
+ * streams.  The rule is mandatory (a flat channel MUST be marked), which keeps streams unique. */
+static uint32_t block_flat_channels(const uint8_t *pixels, uint32_t w, uint32_t c, uint32_t flags, uint32_t x0,
+                                    uint32_t y0, uint32_t bwa, uint32_t bha, uint8_t val[4]) {
+    uint32_t mask = (1u << c) - 1u;
+    const uint8_t *p0 = pixels + ((size_t)y0 * w + x0) * c;
+    for (uint32_t ch = 0; ch < 4; ++ch) val[ch] = ch < c ? xform(p0, c, ch, flags) : 0;
+    for (uint32_t y = 0; y < bha && mask; ++y)
+        for (uint32_t x = 0; x < bwa; ++x) {
+            const uint8_t *p = pixels + ((size_t)(y0 + y) * w + (x0 + x)) * c;
+            for (uint32_t ch = 0; ch < c; ++ch)
+                if (xform(p, c, ch, flags) != val[ch]) mask &= ~(1u << ch);
+        }
+    for (uint32_t ch = 0; ch < 4; ++ch)
+        if (!((mask >> ch) & 1u)) val[ch] = 0;
+    return mask;
 }
 
 size_t flp0_max_stream_bytes(uint32_t w, uint32_t h, uint32_t c, uint32_t bw, uint32_t bh) {
@@ -63,6 +86,22 @@ size_t flp0_block_residuals(const uint8_t *pixels, uint32_t w, uint32_t h, uint3
         }
     }
     return n;
+}
+
+/* Residual histogram of one block with its flat channels left out (what k_histograms emits). */
+uint32_t flp0_block_histogram(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, uint32_t flags,
+                              uint32_t x0, uint32_t y0, uint32_t bw, uint32_t bh, uint32_t hist[256],
+                              uint8_t flat_val[4]) {
+    uint32_t bwa = (w - x0 < bw) ? w - x0 : bw, bha = (h - y0 < bh) ? h - y0 : bh;
+    uint8_t *res = (uint8_t *)malloc((size_t)bw * bh * c);
+    memset(hist, 0, 256 * sizeof(uint32_t));
+    if (!res) return 0;
+    size_t n = flp0_block_residuals(pixels, w, h, c, flags, x0, y0, bw, bh, res);
+    uint32_t flat = block_flat_channels(pixels, w, c, flags, x0, y0, bwa, bha, flat_val);
+    for (size_t i = 0; i < n; ++i)
+        if (!((flat >> (i % c)) & 1u)) hist[res[i]]++;
+    free(res);
+    return flat;
 }
 
 /* (1) sort active symbols by (count, symbol) ascending;
@@ -180,9 +219,12 @@ int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, u
             uint8_t len[256];
             uint16_t code[256];
             size_t n = flp0_block_residuals(pixels, w, h, c, flags, x0, y0, bw, bh, res);
+            uint8_t fval[4];
+            uint32_t flat = block_flat_channels(pixels, w, c, flags, x0, y0, bwa, bha, fval);
 
             memset(hist, 0, sizeof hist);
-            for (size_t i = 0; i < n; ++i) hist[res[i]]++;
+            for (size_t i = 0; i < n; ++i)
+                if (!((flat >> (i % c)) & 1u)) hist[res[i]]++;
             flp0_build_lengths(hist, len);
             flp0_assign_codes(len, code);
 
@@ -199,6 +241,7 @@ int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, u
                     const uint8_t *r = res + (size_t)y * rowsym;
                     for (uint32_t i = 0; i < rowsym; ++i) {
                         uint8_t l = len[r[i]];
+                        if ((flat >> (i % c)) & 1u) continue; /* flat channel: no symbol */
                         if (l != FLP0_LEN_SOLE) bw_put(&b, code[r[i]], l);
                     }
                     bw_flush(&b);
@@ -210,14 +253,17 @@ int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, u
             }
             /* ... §FLP0.6: then the first minw words of the bha real rows are interleaved
              * (word k of row r at k*bha + r) and the rows' tails follow in row order. */
-            uint8_t *o = rw + 2 * bh;
+            uint8_t *fw = rw + 2 * bh; /* flat-channel words: mask, then the four values */
+            put_u32(fw, flat);
+            fw[4] = fval[0]; fw[5] = fval[1]; fw[6] = fval[2]; fw[7] = fval[3];
+            uint8_t *o = fw + 4 * FLATW;
             for (uint32_t k = 0; k < minw; ++k)
                 for (uint32_t y = 0; y < bha; ++y, o += 4) memcpy(o, rowbuf + 4 * ((size_t)y * rowcap + k), 4);
             for (uint32_t y = 0; y < bha; ++y) {
                 memcpy(o, rowbuf + 4 * ((size_t)y * rowcap + minw), 4 * (size_t)(rwc[y] - minw));
                 o += 4 * (size_t)(rwc[y] - minw);
             }
-            wpos += 32u + bh / 2u + total;
+            wpos += 32u + bh / 2u + FLATW + total;
         }
     }
     free(rowbuf);
@@ -269,7 +315,7 @@ int flp0_decode(const uint8_t *s, size_t size, uint8_t *pixels, size_t cap) {
 
     for (uint32_t b = 0; b < nb; ++b) {
         uint32_t off = get_u32(dir + 4 * (size_t)b), end = get_u32(dir + 4 * (size_t)(b + 1));
-        if (off > end || end > pw || end - off < 32u + bh / 2u) { free(lut); return FLP0_E_FORMAT; }
+        if (off > end || end > pw || end - off < 32u + bh / 2u + FLATW) { free(lut); return FLP0_E_FORMAT; }
         const uint8_t *blk = payload + 4 * (size_t)off;
         uint32_t x0 = (b % nbx) * bw, y0 = (b / nbx) * bh;
         uint32_t bwa = (w - x0 < bw) ? w - x0 : bw, bha = (h - y0 < bh) ? h - y0 : bh;
@@ -292,7 +338,10 @@ int flp0_decode(const uint8_t *s, size_t size, uint8_t *pixels, size_t cap) {
             }
         }
         const uint8_t *rw = blk + 128;
-        const uint8_t *body = rw + 2 * bh;
+        const uint8_t *fw = rw + 2 * bh;
+        uint32_t flat = get_u32(fw);
+        if (flat >> c) { free(lut); return FLP0_E_FORMAT; }
+        const uint8_t *body = fw + 4 * FLATW;
         uint32_t minw = 0xFFFFFFFFu, total = 0;
         for (uint32_t y = 0; y < bh; ++y) {
             uint32_t words = get_u16(rw + 2 * y);
@@ -300,7 +349,7 @@ int flp0_decode(const uint8_t *s, size_t size, uint8_t *pixels, size_t cap) {
             if (y < bha && words < minw) minw = words;
             total += words;
         }
-        if (32u + bh / 2u + total > end - off) { free(lut); return FLP0_E_FORMAT; }
+        if (32u + bh / 2u + FLATW + total > end - off) { free(lut); return FLP0_E_FORMAT; }
         const uint8_t *tail = body + 4 * (size_t)minw * bha;
         for (uint32_t y = 0; y < bha; ++y) {
             uint32_t words = get_u16(rw + 2 * y);
@@ -313,6 +362,7 @@ int flp0_decode(const uint8_t *s, size_t size, uint8_t *pixels, size_t cap) {
                     uint8_t t[4];
                     for (uint32_t ch = 0; ch < c; ++ch) {
                         uint8_t r;
+                        if ((flat >> ch) & 1u) { t[ch] = fw[4 + ch]; continue; }
                         if (sole >= 0) r = (uint8_t)sole;
                         else {
                             if (nacc < L) {

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define FLP0_MAGIC 0x30504C46u /* 'F','L','P','0' little-endian */
-#define FLP0_VERSION 2
+#define FLP0_VERSION 3
 #define FLP0_MAX_CODE_LEN 10
 #define FLP0_LEN_SOLE 15 /* nibble value: the block's only symbol, zero-length code */
 #define FLP0_HEADER_BYTES 32
@@ -62,6 +62,12 @@ int flp0_decode(const uint8_t *stream, size_t size, uint8_t *pixels, size_t pixe
 size_t flp0_block_residuals(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c,
                             uint32_t flags, uint32_t x0, uint32_t y0, uint32_t bw, uint32_t bh,
                             uint8_t *res);
+
+/* Residual histogram of one block, flat channels excluded; returns the
+ * flat-channel mask and writes the flat channels' values (0 for the others). */
+uint32_t flp0_block_histogram(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, uint32_t flags,
+                              uint32_t x0, uint32_t y0, uint32_t bw, uint32_t bh, uint32_t hist[256],
+                              uint8_t flat_val[4]);
 
 /* Length-limited Huffman code lengths from a 256-bin histogram. */
 void flp0_build_lengths(const uint32_t hist[256], uint8_t len[256]);

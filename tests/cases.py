@@ -28,6 +28,20 @@ def skewed(w, h, c, seed):
     return (np.cumsum(steps, axis=1) & 255).astype(np.uint8)
 
 
+def with_const(img, **chans):
+    """Force channels to constants (flat channels, FLP0 §2b); e.g. with_const(img, c1=77)."""
+    img = img.copy()
+    for k, v in chans.items():
+        img[..., int(k[1:])] = v
+    return img
+
+
+def alpha_ramp(w, h, seed):
+    img = gradient(w, h, 4, seed)
+    img[..., 3] = (np.arange(w)[None, :] * 255 // max(w - 1, 1)).astype(np.uint8)
+    return img
+
+
 # (name, builder) — sizes chosen so the CPU model finishes each in well under a second
 SMALL = [
     ("c1_512x512x3", lambda: gradient(512, 512, 3, 1)),
@@ -46,4 +60,10 @@ SMALL = [
     ("flat_100x50x3", lambda: flat(100, 50, 3, 200)),
     ("skewed_384x96x4", lambda: skewed(384, 96, 4, 13)),
     ("skewed_128x32x1", lambda: skewed(128, 32, 1, 14)),
+    # flat channels: none (alpha ramp), green only, alpha of gray+alpha, two of four, flat in some blocks only
+    ("alpha_ramp_256x64x4", lambda: alpha_ramp(256, 64, 15)),
+    ("const_g_200x40x3", lambda: with_const(gradient(200, 40, 3, 16), c1=77)),
+    ("const_a_77x45x2", lambda: with_const(gradient(77, 45, 2, 17), c1=255)),
+    ("two_flat_300x70x4", lambda: with_const(gradient(300, 70, 4, 18), c2=9, c3=200)),
+    ("partly_flat_384x64x4", lambda: np.concatenate([gradient(128, 64, 4, 19), noise(256, 64, 4, 20)], axis=1)),
 ]

@@ -20,7 +20,7 @@ import cases  # noqa: E402
 import oracle_binding  # noqa: E402
 
 orc = oracle_binding.Oracle(os.path.join(HERE, "..", "..", "oracle", "libflp0_oracle.so"))
-gold = {"format": "FLP0 v1, block 128x32, max code length 11", "sha256": {}}
+gold = {"format": "FLP0 v3 (flat channels), block 128x32, max code length 10", "sha256": {}}
 for name, build in cases.SMALL:
     for flags in (0x01, 0x11):
         s = orc.encode(build(), flags)

@@ -18,6 +18,8 @@ class Oracle:
         lib.flp0_decode.argtypes = [vp, C.c_size_t, vp, C.c_size_t]
         lib.flp0_block_residuals.restype = C.c_size_t
         lib.flp0_block_residuals.argtypes = [vp] + [u32] * 8 + [vp]
+        lib.flp0_block_histogram.restype = C.c_uint32
+        lib.flp0_block_histogram.argtypes = [vp] + [u32] * 8 + [vp, vp]
         lib.flp0_build_lengths.restype = None
         lib.flp0_build_lengths.argtypes = [vp, vp]
         lib.flp0_assign_codes.restype = None
@@ -54,19 +56,23 @@ class Oracle:
         out = np.zeros(shape, dtype=np.uint8)
         return int(self.lib.flp0_decode(s.ctypes.data, s.size, out.ctypes.data, out.size))
 
-    def block_histograms(self, img, flags=1):
-        """uint16 [n_blocks,256] residual histograms in block raster order."""
+    def block_histograms(self, img, flags=1, with_flat=False):
+        """uint16 [n_blocks,256] residual histograms in block raster order, flat channels excluded;
+        with_flat=True also returns uint32 [n_blocks,2] = (flat mask, packed flat values)."""
         img = np.ascontiguousarray(img, dtype=np.uint8)
         h, w, c = img.shape
         nbx, nby = -(-w // self.BW), -(-h // self.BH)
-        res = np.empty(self.BW * self.BH * 4, dtype=np.uint8)
+        hist = np.zeros(256, dtype=np.uint32)
+        val = np.zeros(4, dtype=np.uint8)
         out = np.zeros((nbx * nby, 256), dtype=np.uint16)
+        meta = np.zeros((nbx * nby, 2), dtype=np.uint32)
         for by in range(nby):
             for bx in range(nbx):
-                n = self.lib.flp0_block_residuals(img.ctypes.data, w, h, c, flags, bx * self.BW, by * self.BH,
-                                                  self.BW, self.BH, res.ctypes.data)
-                out[by * nbx + bx] = np.bincount(res[:n], minlength=256)
-        return out
+                m = self.lib.flp0_block_histogram(img.ctypes.data, w, h, c, flags, bx * self.BW, by * self.BH,
+                                                  self.BW, self.BH, hist.ctypes.data, val.ctypes.data)
+                out[by * nbx + bx] = hist
+                meta[by * nbx + bx] = (m, int(val.view(np.uint32)[0]))
+        return (out, meta) if with_flat else out
 
     def table(self, hist):
         """hist uint[256] -> uint16[256] entries len<<12|code (15<<12 for a sole symbol), as k_tables emits."""

@@ -29,11 +29,13 @@ def test_stage_histograms_and_tables(codec, oracle, name, build, flags):
     nb = -(-img.shape[1] // 128) * -(-img.shape[0] // 32)
     hist = torch.zeros((nb, 256), dtype=torch.int16, device="cuda")
     table = torch.zeros((nb, 256), dtype=torch.int16, device="cuda")
-    codec.stage_histograms(px, hist, flags)
+    flat = torch.zeros((nb, 2), dtype=torch.int32, device="cuda")
+    codec.stage_histograms(px, hist, flags, flat=flat)
     codec.stage_tables(hist, table)
     codec.check()
-    want_h = oracle.block_histograms(img, flags)
+    want_h, want_f = oracle.block_histograms(img, flags, with_flat=True)
     got_h = hist.cpu().numpy().view(np.uint16)
+    assert np.array_equal(flat.cpu().numpy().view(np.uint32), want_f), "flat-channel mask / values"
     assert np.array_equal(got_h, want_h), f"first bad block {np.argwhere((got_h != want_h).any(1))[:1]}"
     got_t = table.cpu().numpy().view(np.uint16)
     for b in range(nb):

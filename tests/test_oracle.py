@@ -36,6 +36,25 @@ def test_golden_streams(oracle):
     assert np.array_equal(oracle.decode(stream, img.shape), img)
 
 
+def test_flat_channels(oracle):
+    """FLP0 §2b: a channel that is constant over a block is named in the block header and costs no bits."""
+    img = cases.gradient(256, 64, 4, 2)                      # alpha = 255 everywhere
+    _, meta = oracle.block_histograms(img, with_flat=True)
+    assert (meta[:, 0] == 8).all() and (meta[:, 1] == 0xFF000000).all()
+    ramp = cases.alpha_ramp(256, 64, 2)
+    _, meta = oracle.block_histograms(ramp, with_flat=True)
+    assert (meta[:, 0] == 0).all()
+    assert len(oracle.encode(img)) < len(oracle.encode(ramp))
+    flat = cases.flat(256, 64, 4)                            # every channel flat: headers only
+    h, meta = oracle.block_histograms(flat, with_flat=True)
+    assert (meta[:, 0] == 15).all() and h.sum() == 0
+    assert len(oracle.encode(flat)) == 32 + 4 * (4 + 1) + 4 * 4 * 50
+    # with subtract-green it is the TRANSFORMED value that must be constant
+    sg = cases.with_const(cases.gradient(128, 32, 3, 3), c0=10)
+    assert oracle.block_histograms(sg, 0x01, with_flat=True)[1][0, 0] == 1
+    assert oracle.block_histograms(sg, 0x11, with_flat=True)[1][0, 0] == 0
+
+
 def test_known_answer_lengths(oracle):
     """Hand-checkable Huffman cases for the length builder."""
     h = np.zeros(256, dtype=np.uint32)
