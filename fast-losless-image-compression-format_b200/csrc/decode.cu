@@ -17,6 +17,8 @@
 namespace flic {
 
 constexpr int kDecWarps = 4;
+// stream lines are pulled into L1 this many chunks of average consumption ahead (measured: 0 -> 2 is -7 %)
+constexpr uint32_t kPrefetchChunks = 2;
 // a one-word refill guarantees 32 buffered bits: that is floor(32 / kL) whole symbols
 constexpr int kSymsPerRefill = 32 / kL;
 
@@ -329,7 +331,7 @@ __device__ __forceinline__ void acc_set(Acc &v, int ch, uint32_t val) {
 // chunks.  FM < 0: any other mask, taken from `fmask` at run time — a plain per-pixel loop (rare blocks).
 template <int C, bool SG, int FM>
 __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel, uint32_t m2048, uint8_t *dst, int bwa,
-                            bool active, int aligned, int lane, uint32_t fmask, uint32_t fvals) {
+                            bool active, int aligned, int lane, uint32_t fmask, uint32_t fvals, uint32_t pfx) {
     constexpr int FMC = FM < 0 ? 0 : FM;
     constexpr int U = Chunk<C, FMC>::U, W = Chunk<C, FMC>::W;
     const uint32_t amask = __ballot_sync(0xFFFFFFFFu, active);
@@ -369,11 +371,18 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
 
     int x = 0;
     if (FM >= 0) {
+        // L1 prefetch distance in stream words: `pfx` chunks' worth of this row's average consumption
+        const uint32_t pf = pfx ? (pfx * rs.words * (uint32_t)U) / (uint32_t)bwa + 2u : 0u;
         for (; x + U <= bwa; x += U) {
             uint32_t o[W];
             // fast path while no lane of the warp can leave the interleaved region inside this chunk
-            if (__all_sync(amask, br.k + (uint32_t)Chunk<C, FMC>::kMaxRefills <= rs.minw))
+            if (__all_sync(amask, br.k + (uint32_t)Chunk<C, FMC>::kMaxRefills <= rs.minw)) {
+                if (pf) {  // pull the interleaved line `pf` words ahead into L1: refills then hit it
+                    const uint32_t kp = min(br.k + pf, rs.minw - 1u);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rs.blk + (rs.ib + kp * rs.stride)));
+                }
                 decode_chunk<C, SG, FMC, true>(br, rs, acc, luts, wsel, m2048, o);
+            }
             else
                 decode_chunk<C, SG, FMC, false>(br, rs, acc, luts, wsel, m2048, o);
             uint8_t *d = dst + (size_t)x * C;
@@ -406,7 +415,7 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
 
 __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *__restrict__ streams,
                                                           const unsigned long long *__restrict__ offsets, Geo g,
-                                                          uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048) {
+                                                          uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048, uint32_t pf) {
     __shared__ __align__(16) uint16_t luts[kDecWarps][kLutSize];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t gb = (uint64_t)blockIdx.x * kDecWarps + warp;
@@ -459,7 +468,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
     const char *lb = reinterpret_cast<const char *>(&luts[0][0]);
     const uint32_t wsel = (uint32_t)warp << 11;
     static_assert(kLutSize * 2 == 2048, "wsel assumes 2 KB per warp LUT");
-#define FLIC_ROWS(C, SG, FM) decode_rows<C, SG, FM>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane, fmask, fvals)
+#define FLIC_ROWS(C, SG, FM) decode_rows<C, SG, FM>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane, fmask, fvals, pf)
     if (fmask == 0) {
         switch (g.c) {
             case 1: FLIC_ROWS(1, false, 0); break;
@@ -484,7 +493,7 @@ void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offset
                    uint8_t *d_pixels, uint32_t *d_err, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
     unsigned grid = (unsigned)((total + kDecWarps - 1) / kDecWarps);
-    k_decode<<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u);
+    k_decode<<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks);
 }
 
 }  // namespace flic
