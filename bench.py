@@ -383,7 +383,7 @@ def main():
         return
 
     hbm, peak_src = peaks()
-    alg = {"k_histograms": raw, "k_tables": 0, "k_pack": raw + comp, "k_finalize": 0, "k_decode": raw + comp}
+    alg = {"k_histograms": raw, "k_tables": 0, "k_slots": 0, "k_pack": raw + comp, "k_finalize": 0, "k_decode": raw + comp}
     kernels = {}
     for k, (ms, cnt) in ktimes.items():
         if cnt:

@@ -61,7 +61,7 @@ def load_library():
         "flic_peek": (i32, [vp, u64, C.POINTER(_Info)]),
         "flic_splice_block_rows": (i32, [C.POINTER(vp), C.POINTER(u64), u32, vp, u64, C.POINTER(u64)]),
         "flic_stage_histograms": (i32, [vp, vp, u32, u32, u32, u32, u32, vp, vp, vp]),
-        "flic_stage_tables": (i32, [vp, vp, u64, vp, vp]),
+        "flic_stage_tables": (i32, [vp, vp, u64, vp, vp, vp]),
         "flic_launch_count": (u64, [vp]),
         "flic_set_kernel_timing": (i32, [vp, i32]),
         "flic_get_kernel_times": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
@@ -80,7 +80,7 @@ EXPORTED = (
     "flic_launch_count flic_set_kernel_timing flic_get_kernel_times"
 ).split()
 
-KERNELS = ("k_histograms", "k_tables", "k_pack", "k_finalize", "k_decode")
+KERNELS = ("k_histograms", "k_tables", "k_pack", "k_finalize", "k_decode", "k_slots")
 
 
 def max_stream_bytes(w, h, c):
@@ -214,5 +214,6 @@ class Codec:
         self._chk(self.lib.flic_stage_histograms(self.h, _ptr(pixels), n, w, h, c, flags, _ptr(hist),
                                                  _ptr(flat) if flat is not None else None, C.c_void_p(stream)))
 
-    def stage_tables(self, hist, table, stream=0):
-        self._chk(self.lib.flic_stage_tables(self.h, _ptr(hist), hist.shape[0], _ptr(table), C.c_void_p(stream)))
+    def stage_tables(self, hist, table, stream=0, bits=None):
+        self._chk(self.lib.flic_stage_tables(self.h, _ptr(hist), hist.shape[0], _ptr(table),
+                                             _ptr(bits) if bits is not None else None, C.c_void_p(stream)))

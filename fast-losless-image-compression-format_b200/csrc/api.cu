@@ -21,7 +21,10 @@ struct flic_ctx {
     uint16_t *d_hist = nullptr, *d_table = nullptr;
     uint32_t *d_resid = nullptr;  // residual plane: 32 rows x 32 lanes x C words (<= 16 KB) per block
     uint2 *d_flat = nullptr;      // per block {flat-channel mask, values}
-    unsigned long long *d_status = nullptr, *d_dirE = nullptr;
+    uint32_t *d_bits = nullptr;             // per block: sum of count x code length
+    unsigned long long *d_dirE = nullptr;   // per block: exclusive prefix sum of slot words (+ grand total)
+    unsigned long long *d_slot_status = nullptr;  // k_slots: 128 epoch-tagged run sums
+    uint32_t slot_epoch = 0;
     uint32_t *d_err = nullptr;
     uint32_t *h_err = nullptr;  // pinned
     // host-API pipeline: chunks of the batch flow H2D -> kernels -> D2H on three streams with
@@ -96,7 +99,7 @@ extern "C" uint64_t flic_blocks_per_image(uint32_t w, uint32_t h) {
 
 extern "C" uint64_t flic_max_stream_bytes(uint32_t w, uint32_t h, uint32_t c) {
     uint64_t nb = flic_blocks_per_image(w, h);
-    uint64_t blk = kBlkHdrWords + (uint64_t)kBH * ((kBW * c * kL + 31) / 32);
+    uint64_t blk = kBlkHdrWords + (uint64_t)kBH * ((kBW * c * kL + 31) / 32 + 1);  // + slot slack: one word per row
     return 4ull * (kHdrWords + nb + 1 + nb * blk);
 }
 
@@ -113,6 +116,8 @@ extern "C" int flic_create(int device, flic_ctx **out) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_err, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_err, 0, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_slot_status, 128 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_slot_status, 0, 128 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_err, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
@@ -133,8 +138,8 @@ extern "C" int flic_create(int device, flic_ctx **out) {
 extern "C" void flic_destroy(flic_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_status); cudaFree(ctx->d_dirE);
-    cudaFree(ctx->d_resid); cudaFree(ctx->d_flat); cudaFree(ctx->d_err);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_bits); cudaFree(ctx->d_dirE);
+    cudaFree(ctx->d_resid); cudaFree(ctx->d_flat); cudaFree(ctx->d_err); cudaFree(ctx->d_slot_status);
     for (int i = 0; i < 2; ++i) {
         cudaFree(ctx->d_pix[i]); cudaFree(ctx->d_str[i]); cudaFree(ctx->d_off[i]);
         if (ctx->h_off[i]) cudaFreeHost(ctx->h_off[i]);
@@ -153,15 +158,15 @@ extern "C" void flic_destroy(flic_ctx *ctx) {
 
 static int ensure_workspace(flic_ctx *ctx, uint64_t blocks) {
     if (blocks <= ctx->ws_blocks) return FLIC_OK;
-    cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_status); cudaFree(ctx->d_dirE);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_bits); cudaFree(ctx->d_dirE);
     cudaFree(ctx->d_resid); cudaFree(ctx->d_flat);
-    ctx->d_hist = ctx->d_table = nullptr; ctx->d_status = ctx->d_dirE = nullptr; ctx->d_resid = nullptr; ctx->d_flat = nullptr;
+    ctx->d_hist = ctx->d_table = nullptr; ctx->d_bits = nullptr; ctx->d_dirE = nullptr; ctx->d_resid = nullptr; ctx->d_flat = nullptr;
     ctx->ws_blocks = 0;
     CU(cudaMalloc(&ctx->d_resid, blocks * (uint64_t)kBH * 512));
     CU(cudaMalloc(&ctx->d_flat, blocks * sizeof(uint2)));
     CU(cudaMalloc(&ctx->d_hist, blocks * 256 * sizeof(uint16_t)));
     CU(cudaMalloc(&ctx->d_table, blocks * 256 * sizeof(uint16_t)));
-    CU(cudaMalloc(&ctx->d_status, (blocks + 1) * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ctx->d_bits, blocks * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_dirE, (blocks + 1) * sizeof(unsigned long long)));
     ctx->ws_blocks = blocks;
     return FLIC_OK;
@@ -194,10 +199,10 @@ extern "C" int flic_stage_histograms(flic_ctx *ctx, const uint8_t *d_pixels, uin
 }
 
 extern "C" int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t n_blocks_total, uint16_t *d_table,
-                                 void *stream) {
+                                 uint32_t *d_bits, void *stream) {
     if (!ctx || !d_hist || !d_table || n_blocks_total == 0) return FLIC_E_ARG;
     CU(cudaSetDevice(ctx->device));
-    { KernelTimer t(ctx, FLIC_K_TABLES, (cudaStream_t)stream); launch_tables(d_hist, n_blocks_total, d_table, (cudaStream_t)stream); }
+    { KernelTimer t(ctx, FLIC_K_TABLES, (cudaStream_t)stream); launch_tables(d_hist, n_blocks_total, d_table, d_bits, (cudaStream_t)stream); }
     ctx->launches += 1;
     CU(cudaGetLastError());
     return FLIC_OK;
@@ -217,13 +222,13 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
     cudaStream_t s = (cudaStream_t)stream;
     const uint64_t cap_words = capacity_bytes / 4;
     { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s); launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, ctx->d_flat, s); }
-    { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, (uint64_t)n * g.nb, ctx->d_table, s); }
-    CU(cudaMemsetAsync(ctx->d_status, 0, ((uint64_t)n * g.nb + 1) * sizeof(unsigned long long), s));
+    { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, (uint64_t)n * g.nb, ctx->d_table, ctx->d_bits, s); }
+    { KernelTimer t(ctx, FLIC_K_SLOTS, s); launch_slots(g, ctx->d_bits, ctx->d_dirE, ctx->d_slot_status, ++ctx->slot_epoch, cap_words, ctx->d_err, s); }
     { KernelTimer t(ctx, FLIC_K_PACK, s);
-      launch_pack(ctx->d_resid, g, ctx->d_table, ctx->d_flat, (uint32_t *)d_streams, cap_words, ctx->d_status, ctx->d_dirE, ctx->d_err, s); }
+      launch_pack(ctx->d_resid, g, ctx->d_table, ctx->d_flat, (uint32_t *)d_streams, cap_words, ctx->d_dirE, ctx->d_err, s); }
     { KernelTimer t(ctx, FLIC_K_FINALIZE, s);
       launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s); }
-    ctx->launches += 4;
+    ctx->launches += 5;
     CU(cudaGetLastError());
     return FLIC_OK;
 }
@@ -275,7 +280,7 @@ extern "C" int flic_check(flic_ctx *ctx, void *stream) {
     uint32_t e = *ctx->h_err;
     if (!e) return FLIC_OK;
     snprintf(ctx->msg, sizeof ctx->msg, "device error bits 0x%x%s%s%s", e, (e & kErrCapacity) ? " capacity" : "",
-             (e & kErrWatchdog) ? " look-back-watchdog" : "", (e & kErrFormat) ? " format" : "");
+             (e & kErrSlot) ? " slot-overrun" : "", (e & kErrFormat) ? " format" : "");
     if (e & kErrFormat) return FLIC_E_FORMAT;
     if (e & kErrCapacity) return FLIC_E_CAPACITY;
     return FLIC_E_INTERNAL;

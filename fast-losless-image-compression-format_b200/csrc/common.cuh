@@ -26,8 +26,8 @@ constexpr uint32_t kLenSole = 15;
 
 // device-side error bits, OR-ed into ctx->d_err[0]
 constexpr uint32_t kErrCapacity = 1u;
-constexpr uint32_t kErrWatchdog = 2u;
 constexpr uint32_t kErrFormat = 4u;
+constexpr uint32_t kErrSlot = 8u;  // a block outgrew the slot k_slots computed for it (internal error)
 
 struct Geo {
     uint32_t n, w, h, c, flags;
@@ -167,10 +167,11 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 // launchers (defined in the .cu files, used by api.cu)
 void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, uint2 *d_flat,
                        cudaStream_t s);
-void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, cudaStream_t s);
+void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s);
+void launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_dirE, unsigned long long *d_status,
+                  uint32_t epoch, uint64_t capacity_words, uint32_t *d_err, cudaStream_t s);
 void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, const uint2 *d_flat, uint32_t *d_streams,
-                 uint64_t capacity_words, unsigned long long *d_status, unsigned long long *d_dirE,
-                 uint32_t *d_err, cudaStream_t s);
+                 uint64_t capacity_words, const unsigned long long *d_dirE, uint32_t *d_err, cudaStream_t s);
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,
                      uint64_t capacity_words, unsigned long long *d_offsets, uint32_t *d_err,
                      cudaStream_t s);

@@ -294,8 +294,10 @@ __device__ __forceinline__ void sort_block(uint32_t *key, int n, uint16_t *Arow,
     }
 }
 
+// bits (optional): per block, the sum over symbols of count x code length — with the geometry that is
+// the block's slot size (FLP0 §7), so every block's output position is known before k_pack runs.
 __global__ void __launch_bounds__(32) k_tables(const uint16_t *__restrict__ hist, uint64_t nblocks,
-                                               uint16_t *__restrict__ table, int bpw) {
+                                               uint16_t *__restrict__ table, uint32_t *__restrict__ bits, int bpw) {
     __shared__ __align__(16) TabSmem s;
     const int lane = threadIdx.x;
     const uint64_t first = (uint64_t)blockIdx.x * bpw;
@@ -373,6 +375,16 @@ __global__ void __launch_bounds__(32) k_tables(const uint16_t *__restrict__ hist
             if (lane >= d) { ia += ta; ib += tb; }
         }
         uint64_t ea = ia - ca, eb = ib - cb;  // symbols of each length in lower lanes
+        if (bits) {
+            const uint4 hv = *reinterpret_cast<const uint4 *>(hist + (first + j) * 256 + 8 * lane);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+            uint32_t b = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (l8[k] <= (uint32_t)kL) b += ((hw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu) * l8[k];
+            b = __reduce_add_sync(0xFFFFFFFFu, b);
+            if (lane == 0) bits[first + j] = b;
+        }
         uint32_t out[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -390,86 +402,95 @@ __global__ void __launch_bounds__(32) k_tables(const uint16_t *__restrict__ hist
     }
 }
 
-void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, cudaStream_t s) {
+void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s) {
     // a few blocks per warp when that still fills the chip; kTabBpw (merge lanes busy) for large jobs
     uint64_t want = nblocks / (148ull * 16);
     int bpw = (int)(want < 2 ? 2 : (want > kTabBpw ? kTabBpw : want));
     unsigned grid = (unsigned)((nblocks + bpw - 1) / bpw);
-    k_tables<<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, bpw);
+    k_tables<<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
+}
+
+// ---------------------------------------------------------------------- k_slots
+// FLP0 §7: slot(block) = block header + floor(code bits / 32) + one word per real row (none without code
+// bits); dirE = exclusive prefix sum over all blocks of the batch (dirE[total] = grand total).
+// Half a megabyte of input, so latency is all that matters: at most 128 co-resident CTAs each own a
+// contiguous run of blocks, publish the run's sum tagged with this launch's epoch (no memset between
+// launches), sum their predecessors' published values, then scan their own run.
+constexpr int kSlotThreads = 1024;
+__device__ __forceinline__ uint32_t slot_words(uint32_t code_bits, uint32_t b, uint32_t last_row_first, uint32_t last_bha) {
+    return (uint32_t)kBlkHdrWords + (code_bits >> 5) + (code_bits ? (b >= last_row_first ? last_bha : (uint32_t)kBH) : 0u);
+}
+__global__ void __launch_bounds__(kSlotThreads) k_slots(Geo g, const uint32_t *__restrict__ bits,
+                                                        unsigned long long *__restrict__ dirE, uint32_t per,
+                                                        uint32_t epoch, unsigned long long *status,
+                                                        uint64_t capacity_words, uint32_t *err) {
+    __shared__ uint32_t wsum[32];
+    __shared__ unsigned long long s_excl;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t total = (uint64_t)g.n * g.nb;
+    const uint64_t lo = (uint64_t)blockIdx.x * per, hi = min(total, lo + per);
+    const uint32_t last_row_first = (g.nby - 1) * g.nbx, last_bha = g.h - (g.nby - 1) * kBH;
+    // pass 1: the run's sum
+    uint32_t sum = 0;
+    for (uint64_t gb = lo + tid; gb < hi; gb += kSlotThreads)
+        sum += slot_words(__ldg(bits + gb), (uint32_t)(gb % g.nb), last_row_first, last_bha);
+    sum = __reduce_add_sync(0xFFFFFFFFu, sum);
+    if (lane == 0) wsum[warp] = sum;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t agg = __reduce_add_sync(0xFFFFFFFFu, wsum[lane]);
+        if (lane == 0) {
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(status + blockIdx.x),
+                         "l"(((unsigned long long)epoch << 32) | agg) : "memory");
+        }
+        unsigned long long excl = 0;
+        for (uint32_t i = lane; i < blockIdx.x; i += 32) {
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(status + i) : "memory");
+            } while ((uint32_t)(v >> 32) != epoch);
+            excl += (uint32_t)v;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const uint32_t l = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)excl, d), h = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(excl >> 32), d);
+            excl += ((unsigned long long)h << 32) | l;
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    // pass 2: exclusive scan of the run, 1024 blocks per step (the second read of `bits` hits L2)
+    unsigned long long carry = s_excl;
+    for (uint64_t base = lo; base < hi; base += kSlotThreads) {
+        const uint64_t gb = base + tid;
+        const uint32_t v = gb < hi ? slot_words(__ldg(bits + gb), (uint32_t)(gb % g.nb), last_row_first, last_bha) : 0u;
+        const uint32_t incl = warp_incl_scan(v, lane);
+        __syncthreads();
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        const uint32_t w = wsum[lane];
+        const uint32_t wincl = warp_incl_scan(w, lane);
+        const uint32_t before = __shfl_sync(0xFFFFFFFFu, wincl - w, warp);
+        if (gb < hi) dirE[gb] = carry + before + (incl - v);
+        carry += __shfl_sync(0xFFFFFFFFu, wincl, 31);
+    }
+    if (hi == total && tid == 0) {
+        dirE[total] = carry;
+        if ((uint64_t)g.n * (kHdrWords + (uint64_t)g.nb + 1) + carry > capacity_words) atomicOr(err, kErrCapacity);
+    }
+}
+
+// status: >= 128 u64, zeroed once at allocation; epoch: a value never used before on this status array (>= 1)
+void launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_dirE, unsigned long long *d_status,
+                  uint32_t epoch, uint64_t capacity_words, uint32_t *d_err, cudaStream_t s) {
+    const uint64_t total = (uint64_t)g.n * g.nb;
+    uint64_t per = (total + 127) / 128;
+    per = ((per < 2048 ? 2048 : per) + kSlotThreads - 1) / kSlotThreads * kSlotThreads;
+    const unsigned grid = (unsigned)((total + per - 1) / per);  // <= 128: all CTAs are resident, the spin cannot deadlock
+    k_slots<<<grid, kSlotThreads, 0, s>>>(g, d_bits, d_dirE, (uint32_t)per, epoch, d_status, capacity_words, d_err);
 }
 
 // ---------------------------------------------------------------------- k_pack
-constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValMask = (1ull << 62) - 1;
-constexpr uint32_t kSpinLimit = 1u << 22;
-
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
-}
-
-// Single-pass chained scan (decoupled look-back) over block payload sizes, run by warp 0 as a
-// resumable state machine: start() publishes this block's aggregate as soon as its size is
-// known (before any packing), poll() makes non-blocking progress between rows of packing, and
-// finish() blocks only if predecessors still have not published.  Blocks are claimed in ticket
-// order, so every predecessor is already running and the wait is bounded (watchdog otherwise).
-struct Lookback {
-    unsigned long long *status;
-    uint64_t gb;
-    long long idx;
-    unsigned long long excl;
-    uint32_t size;
-    bool done;
-
-    __device__ __forceinline__ void start(unsigned long long *st, uint64_t gb_, uint32_t size_, int lane) {
-        status = st; gb = gb_; size = size_; idx = (long long)gb_ - 1; excl = 0; done = false;
-        if (lane == 0) st_status(status + gb, kFlagAgg | size);
-        if (idx < 0) publish(lane);
-    }
-    __device__ __forceinline__ void publish(int lane) {
-        done = true;
-        if (lane == 0) st_status(status + gb, kFlagPrefix | ((excl + size) & kValMask));
-    }
-    // consumes every 32-block window that is fully published; returns when one is not.  With ~1200 blocks
-    // in flight a look-back walks tens of windows, so a window is kept to a dozen instructions: block
-    // sizes fit 32 bits and are summed by one REDUX; only a found prefix needs its 62-bit value moved.
-    __device__ __forceinline__ void poll(int lane) {
-        while (!done) {
-            const long long my = idx - lane;
-            const unsigned long long v = my >= 0 ? ld_status(status + my) : kFlagPrefix;
-            const uint32_t flag = (uint32_t)(v >> 62);
-            if (__any_sync(0xFFFFFFFFu, flag == 0)) return;
-            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, flag == 2);
-            const int first = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor holding an inclusive prefix
-            excl += __reduce_add_sync(0xFFFFFFFFu, lane < first ? (uint32_t)v : 0u);
-            if (pm) {
-                const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)v, first);
-                const uint32_t hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)((v & kValMask) >> 32), first);
-                excl += ((unsigned long long)hi << 32) | lo;
-                publish(lane);
-            } else {
-                idx -= 32;
-            }
-        }
-    }
-    __device__ __forceinline__ void finish(int lane, uint32_t *err) {
-        uint32_t spins = 0;
-        while (!done) {
-            poll(lane);
-            if (!done) {
-                __nanosleep(64);  // a predecessor is still packing: do not burn issue slots other CTAs can use
-                if (++spins >= kSpinLimit) {
-                    if (lane == 0) atomicOr(err, kErrWatchdog);
-                    publish(lane);
-                }
-            }
-        }
-    }
-};
-
 // Staging tile: per row 3 pad words (they absorb the all-zero upper words of a code group placed at
 // the very start of a row) + kRowWordsMax data words; the pitch is odd, so the interleaving copy-out
 // reads a column conflict-free.
@@ -524,27 +545,21 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
                                                       const uint16_t *__restrict__ table,
                                                       const uint2 *__restrict__ flat,
                                                       uint32_t *__restrict__ streams, uint64_t capacity_words,
-                                                      unsigned long long *status, unsigned long long *dirE,
+                                                      const unsigned long long *__restrict__ dirE,
                                                       uint32_t *err, PackMul pm) {
     __shared__ __align__(16) uint32_t stage[kBH * kStagePitch];
     __shared__ uint32_t tab[256];  // code | len << 24; 0 for a sole symbol (no bits)
     __shared__ uint8_t nib[256];
     __shared__ uint32_t rwc[kBH], rowoff[kBH];
-    __shared__ unsigned long long s_gb, s_base;
-    __shared__ uint32_t s_minw;
+    __shared__ uint32_t s_minw, s_used;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint64_t total_blocks = (uint64_t)g.n * g.nb;
-
-    // blocks are claimed in launch order so that look-back predecessors are always resident or done
-    if (tid == 0) s_gb = atomicAdd(status + total_blocks, 1ull);
+    const uint64_t gb = blockIdx.x;
+    const BlockPos p = block_pos(g, gb);
     {
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *s4 = reinterpret_cast<uint4 *>(stage);
         for (int i = tid; i < kBH * kStagePitch / 4; i += kEncThreads) s4[i] = z;
     }
-    __syncthreads();
-    const uint64_t gb = s_gb;
-    const BlockPos p = block_pos(g, gb);
 
     {
         uint32_t e = table[gb * 256 + tid], l = e >> 12;
@@ -612,8 +627,11 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     }
     __syncthreads();
 
-    Lookback lb;
-    uint32_t size = 0;
+    // FLP0 §7: the block's slot (position and size) was fixed by k_slots from the histogram and the code
+    // lengths, so there is nothing to wait for: no ordering between blocks, no look-back.
+    const unsigned long long excl = dirE[gb];
+    const uint32_t slot = (uint32_t)(dirE[gb + 1] - excl);
+    const unsigned long long base = (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + excl;
     if (warp == 0) {
         const uint32_t wcount = rwc[lane];
         const uint32_t incl = warp_incl_scan(wcount, lane);
@@ -621,27 +639,21 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
         uint32_t mn = lane < (int)p.bha ? wcount : 0xFFFFFFFFu;  // FLP0 §6: interleave depth
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
-        if (lane == 0) s_minw = mn;
-        size = kBlkHdrWords + __shfl_sync(0xFFFFFFFFu, incl, 31);
-        lb.start(status, gb, size, lane);
-    }
-    if (warp == 0) {
-        lb.finish(lane, err);
+        const uint32_t used = kBlkHdrWords + __shfl_sync(0xFFFFFFFFu, incl, 31);
         if (lane == 0) {
-            const unsigned long long excl = lb.excl;
-            dirE[gb] = excl;
-            if (gb == total_blocks - 1) dirE[total_blocks] = excl + size;
-            unsigned long long base = (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + excl;
-            if (base + size > capacity_words) {
-                atomicOr(err, kErrCapacity);
-                base = ~0ull;
-            }
-            s_base = base;
+            s_minw = mn;
+            s_used = used;
+            if (used > slot) atomicOr(err, kErrSlot);  // cannot happen: rows pad by less than a word each
         }
     }
     __syncthreads();
-    if (s_base == ~0ull) return;
-    uint32_t *out = streams + s_base;
+    if (s_used > slot) return;
+    if (base + slot > capacity_words) {
+        if (tid == 0) atomicOr(err, kErrCapacity);
+        return;
+    }
+    uint32_t *out = streams + base;
+    for (uint32_t i = s_used + tid; i < slot; i += kEncThreads) out[i] = 0u;  // slack of the slot
     if (warp == 0) {
         uint32_t v = 0;
 #pragma unroll
@@ -678,12 +690,11 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
 }
 
 void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, const uint2 *d_flat, uint32_t *d_streams,
-                 uint64_t capacity_words, unsigned long long *d_status, unsigned long long *d_dirE,
-                 uint32_t *d_err, cudaStream_t s) {
-    uint64_t total = (uint64_t)g.n * g.nb;  // caller has zeroed d_status[0..total] on this stream
+                 uint64_t capacity_words, const unsigned long long *d_dirE, uint32_t *d_err, cudaStream_t s) {
+    uint64_t total = (uint64_t)g.n * g.nb;
     const PackMul pm = {1u << 8, 1u << 10, 1u << 18, 1u << 26};
 #define FLIC_PACK(C) \
-    k_pack<C><<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_flat, d_streams, capacity_words, d_status, d_dirE, d_err, pm)
+    k_pack<C><<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_flat, d_streams, capacity_words, d_dirE, d_err, pm)
     switch (g.c) {
         case 1: FLIC_PACK(1); break;
         case 2: FLIC_PACK(2); break;

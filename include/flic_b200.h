@@ -84,7 +84,7 @@ int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams, const uint
 
 /* Synchronises `stream` and reports device-side error flags raised by the
  * kernels launched through ctx since the last check (capacity overrun,
- * corrupt directory, look-back watchdog). */
+ * corrupt directory, slot overrun). */
 int flic_check(flic_ctx *ctx, void *stream);
 
 /* ---- host-buffer batch API (H2D + kernels + D2H inside the call) ------- */
@@ -113,9 +113,10 @@ int flic_stage_histograms(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t n, ui
                           uint32_t h, uint32_t c, uint32_t flags, uint16_t *d_hist,
                           uint32_t *d_flat, void *stream);
 /* Per-block code tables from histograms: d_table[n_blocks_total][256] u16,
- * entry = len << 12 | code (len 15 = sole symbol). */
+ * entry = len << 12 | code (len 15 = sole symbol); d_bits (may be NULL): [n_blocks_total] u32 =
+ * sum over symbols of count x code length (what fixes a block's slot size). */
 int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t n_blocks_total,
-                      uint16_t *d_table, void *stream);
+                      uint16_t *d_table, uint32_t *d_bits, void *stream);
 
 /* ---- measurement hooks (bench.py) --------------------------------------- */
 #define FLIC_K_HISTOGRAMS 0
@@ -123,7 +124,8 @@ int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t n_blocks_t
 #define FLIC_K_PACK 2
 #define FLIC_K_FINALIZE 3
 #define FLIC_K_DECODE 4
-#define FLIC_K_COUNT 5
+#define FLIC_K_SLOTS 5
+#define FLIC_K_COUNT 6
 /* When enabled, every kernel launched through ctx is bracketed by CUDA events
  * recorded on the launching stream.  flic_get_kernel_times() waits for the
  * recorded events, returns summed milliseconds and launch counts per kernel

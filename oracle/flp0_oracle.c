@@ -31,8 +31,14 @@ static inline uint8_t xform(const uint8_t *px, uint32_t c, uint32_t ch, uint32_t
 /* per-block payload bound = 32 length words + bh/2 row-count
  * words + 2 flat-channel words + bh rows of ceil(bw*c*L/32) words. */
 #define FLATW 2u
+/* a block occupies a SLOT whose size follows from its histogram and code
+ * lengths alone — header + floor(total code bits / 32) + one word per real row (none if there
+ * are no code bits at all) — so that every
+ * block's position is known before any bit is packed (no serial dependence between blocks in the
+ * encoder).  Rows are word-aligned, so the payload needs at most that; the rest of the slot is
+ * zero. */
 static size_t block_max_words(uint32_t c, uint32_t bw, uint32_t bh) {
-    return 32u + bh / 2u + FLATW + (size_t)bh * ceil_div(bw * c * L, 32u);
+    return 32u + bh / 2u + FLATW + (size_t)bh * (ceil_div(bw * c * L, 32u) + 1u);
 }
 
 /* a channel is FLAT in a block when every pixel of the block has the same
@@ -253,6 +259,10 @@ int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, u
             }
             /* ... §FLP0.6: then the first minw words of the bha real rows are interleaved
              * (word k of row r at k*bha + r) and the rows' tails follow in row order. */
+            uint64_t code_bits = 0;
+            for (int sy = 0; sy < 256; ++sy)
+                if (len[sy] >= 1 && len[sy] <= L) code_bits += (uint64_t)hist[sy] * len[sy];
+            uint32_t slot = 32u + bh / 2u + FLATW + (uint32_t)(code_bits >> 5) + (code_bits ? bha : 0u);
             uint8_t *fw = rw + 2 * bh; /* flat-channel words: mask, then the four values */
             put_u32(fw, flat);
             fw[4] = fval[0]; fw[5] = fval[1]; fw[6] = fval[2]; fw[7] = fval[3];
@@ -263,7 +273,9 @@ int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, u
                 memcpy(o, rowbuf + 4 * ((size_t)y * rowcap + minw), 4 * (size_t)(rwc[y] - minw));
                 o += 4 * (size_t)(rwc[y] - minw);
             }
-            wpos += 32u + bh / 2u + FLATW + total;
+            /* zero the slack up to the block's slot */
+            memset(o, 0, 4 * (size_t)(slot - (32u + bh / 2u + FLATW + total)));
+            wpos += slot;
         }
     }
     free(rowbuf);

@@ -31,15 +31,20 @@ def test_stage_histograms_and_tables(codec, oracle, name, build, flags):
     table = torch.zeros((nb, 256), dtype=torch.int16, device="cuda")
     flat = torch.zeros((nb, 2), dtype=torch.int32, device="cuda")
     codec.stage_histograms(px, hist, flags, flat=flat)
-    codec.stage_tables(hist, table)
+    bits = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    codec.stage_tables(hist, table, bits=bits)
     codec.check()
     want_h, want_f = oracle.block_histograms(img, flags, with_flat=True)
     got_h = hist.cpu().numpy().view(np.uint16)
     assert np.array_equal(flat.cpu().numpy().view(np.uint32), want_f), "flat-channel mask / values"
     assert np.array_equal(got_h, want_h), f"first bad block {np.argwhere((got_h != want_h).any(1))[:1]}"
     got_t = table.cpu().numpy().view(np.uint16)
+    got_b = bits.cpu().numpy()
     for b in range(nb):
-        assert np.array_equal(got_t[b], oracle.table(want_h[b])), f"block {b}"
+        want_t = oracle.table(want_h[b])
+        assert np.array_equal(got_t[b], want_t), f"block {b}"
+        ln = (want_t >> 12).astype(np.int64)
+        assert got_b[b] == int((want_h[b].astype(np.int64) * np.where(ln <= 10, ln, 0)).sum()), f"code bits of block {b}"
 
 
 @pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
