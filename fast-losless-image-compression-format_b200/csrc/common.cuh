@@ -138,12 +138,24 @@ __device__ __forceinline__ void lane_residuals(uint32_t (&v)[C], uint32_t up, in
 }
 
 // Transformed pixel above the block row's first pixel, packed in the low C bytes (lane 0 only).
+// word_ok: the image is 16-byte aligned, so an RGBA / GA pixel can be read as one word / halfword.
 template <int C, bool SG>
-__device__ __forceinline__ uint32_t up_pixel(const uint8_t *row, uint64_t pitch) {
+__device__ __forceinline__ uint32_t up_pixel(const uint8_t *row, uint64_t pitch, bool word_ok) {
     const uint8_t *u = row - pitch;
-    uint32_t b0 = __ldg(u), b1 = C > 1 ? __ldg(u + 1) : 0u, b2 = C > 2 ? __ldg(u + 2) : 0u, b3 = C > 3 ? __ldg(u + 3) : 0u;
-    if (SG && C >= 3) { b0 = (b0 - b1) & 0xFFu; b2 = (b2 - b1) & 0xFFu; }
-    return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    uint32_t v;
+    if (C == 4 && word_ok) v = __ldg(reinterpret_cast<const uint32_t *>(u));
+    else if (C == 2 && word_ok) v = __ldg(reinterpret_cast<const uint16_t *>(u));
+    else {
+        v = __ldg(u);
+        if (C > 1) v |= (uint32_t)__ldg(u + 1) << 8;
+        if (C > 2) v |= (uint32_t)__ldg(u + 2) << 16;
+        if (C > 3) v |= (uint32_t)__ldg(u + 3) << 24;
+    }
+    if (SG && C >= 3) {
+        const uint32_t g = (v >> 8) & 0xFFu;
+        v = __vsub4(v, g | (g << 16));
+    }
+    return v;
 }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {

@@ -48,13 +48,17 @@ template <int C, bool SG>
 __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__restrict__ pixels, Geo g,
                                                             uint16_t *__restrict__ hist, uint32_t *__restrict__ resid,
                                                             uint2 *__restrict__ flat) {
-    __shared__ uint32_t sh[kEncWarps][256];
+    __shared__ __align__(16) uint32_t sh[kEncWarps][256];
     __shared__ uint32_t s_or[C], s_first;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t gb = blockIdx.x;
     const BlockPos p = block_pos(g, gb);
 
-    for (int i = tid; i < kEncWarps * 256; i += kEncThreads) (&sh[0][0])[i] = 0;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(&sh[0][0]);
+#pragma unroll
+        for (int i = 0; i < kEncWarps * 256 / 4 / kEncThreads; ++i) z[tid + i * kEncThreads] = make_uint4(0, 0, 0, 0);
+    }
     if (tid < C) s_or[tid] = 0;
 
     uint32_t res[kBH / kEncWarps][C];
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
         if (r < (int)p.bha) {  // warp-uniform
             uint32_t v[C];
             load_lane_pixels<C>(row, lane, (int)p.bwa, fast, v, &nv[q]);
-            const uint32_t up = (lane == 0 && r > 0) ? up_pixel<C, SG>(row, g.pitch) : 0u;
+            const uint32_t up = (lane == 0 && r > 0) ? up_pixel<C, SG>(row, g.pitch, fast) : 0u;
             lane_residuals<C, SG>(v, up, lane, res[q]);
 #pragma unroll
             for (int j = 0; j < C; ++j) {
