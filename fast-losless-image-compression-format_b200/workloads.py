@@ -56,6 +56,7 @@ CONFIGS = {
     # id: (n_images, w, h, c, kind, first_seed)
     "C1": (1, 512, 512, 3, "gradient", 1),
     "C2": (1, 3840, 2160, 4, "gradient", 2),
+    "C2A": (1, 3840, 2160, 4, "gradient-alpha", 2),  # SURVEY §8(d)'s second variant: alpha is a gradient too
     "C3": (1024, 1920, 1080, 3, "gradient", 1000),
     "C4": (1, 16384, 16384, 4, "gradient", 4),
     "C5": (64, 3840, 2160, 4, "uniform", 5000),
@@ -69,7 +70,12 @@ def make_batch(cfg, n=None, distinct=8):
     n_cfg, w, h, c, kind, seed0 = CONFIGS[cfg]
     n = n_cfg if n is None else n
     k = min(n, distinct)
-    gen = (lambda s: gradient_noise(w, h, c, s)) if kind == "gradient" else (lambda s: uniform_noise(w, h, c, s))
+    if kind == "gradient":
+        gen = lambda s: gradient_noise(w, h, c, s)
+    elif kind == "gradient-alpha":
+        gen = lambda s: gradient_noise(w, h, c, s, alpha="ramp")
+    else:
+        gen = lambda s: uniform_noise(w, h, c, s)
     uniq = [gen(seed0 + i) for i in range(k)]
     out = np.empty((n, h, w, c), dtype=np.uint8)
     for i in range(n):

@@ -132,6 +132,14 @@ def test_errors_through_the_abi(codec, oracle):
     with pytest.raises(flic.FlicError) as e:
         codec.decode(bad)
     assert e.value.code == -3
+    # a flat-channel mask naming a channel the image does not have (block header word 48 of block 0)
+    nb = int(np.frombuffer(s[20:24], np.uint32)[0])
+    first_block = 32 + 4 * (nb + 1) + 4 * int(np.frombuffer(s[32:36], np.uint32)[0])
+    bad = s.copy(); bad[first_block + 4 * 48] = 0x08
+    with pytest.raises(flic.FlicError) as e:
+        codec.decode(bad)
+    assert e.value.code == -3
+    assert oracle.decode_rc(bad, img.shape) == -3
     # device capacity overrun is caught by the kernels, not by an out-of-bounds write
     px = dev(cases.noise(256, 64, 4, 1)[None])
     small = torch.zeros(4096, dtype=torch.uint8, device="cuda")
@@ -185,12 +193,27 @@ def test_c3_batch_slice_roundtrip(codec):
         assert np.array_equal(s[int(off[i]): int(off[i + 1])], s[int(off[i - 8]): int(off[i - 7])])
 
 
+def test_4k_rgba_alpha_variants(codec, oracle):
+    """configs[1] with the three kinds of alpha plane: opaque (flat channel, three symbols per pixel), a
+    ramp (four symbols per pixel), and opaque except for one block (both decode paths in one launch)."""
+    import flic_b200 as flic
+    base = flic.workloads.make_batch("C2")[0]
+    ramp = base.copy(); ramp[..., 3] = (np.arange(base.shape[1])[None, :] * 255 // (base.shape[1] - 1)).astype(np.uint8)
+    spot = base.copy(); spot[40:50, 200:230, 3] = 7
+    imgs = np.stack([base, ramp, spot])
+    streams, off = _roundtrip_device(codec, imgs)
+    sizes = np.diff(off)
+    assert sizes[0] < sizes[2] < sizes[1]
+    got = streams[int(off[2]): int(off[3])].cpu().numpy()
+    assert np.array_equal(got, oracle.encode(spot))
+
+
 def test_c5_uniform_noise_roundtrip(codec):
     import flic_b200 as flic
     imgs = flic.workloads.make_batch("C5", n=4)
     _, off = _roundtrip_device(codec, imgs)
     ratio = float(off[-1]) / imgs.size
-    assert 1.0 < ratio < 1.03  # incompressible input: 8-bit codes + 1.6 % block headers
+    assert 1.0 < ratio < 1.03  # incompressible input: 8-bit codes + 1.2 % block headers + 0.8 % slot slack
 
 
 def test_c4_strip_roundtrip(codec):
