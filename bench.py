@@ -395,10 +395,10 @@ def main():
     # DRAM bytes per launch from the committed ncu capture of this same workload (profiles/), if there is one
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic_c2x64.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01s2_traffic_c2x64.json")) as f:
             tj = json.load(f)
         if tj.get("workload") == args.workload and dom in tj["kernels"]:
-            traffic, traffic_src = tj["kernels"][dom]["traffic_bytes"], "profiles/r01_traffic_c2x64.json (ncu dram__bytes_read+write per launch)"
+            traffic, traffic_src = tj["kernels"][dom]["traffic_bytes"], "profiles/r01s2_traffic_c2x64.json (ncu dram__bytes_read+write per launch)"
             for k in kernels:
                 if k in tj["kernels"]:
                     kernels[k]["dram_traffic_bytes"] = tj["kernels"][k]["traffic_bytes"]
@@ -409,7 +409,7 @@ def main():
         ach = alg[dom] / (kernels[dom]["avg_ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
                 "frac": round(ach / hbm, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "note": "kernels are integer-ALU/latency bound, not HBM bound (profiles/r01_ncu_full_final.txt)",
+                "note": "k_decode: LSU data pipe ~72 % busy (LUT reads), ALU pipe ~50 %; not HBM bound (profiles/r01s2_ncu_full_c2x8.txt)",
                 "algorithmic_bytes_per_launch": alg[dom],
                 "encode_path_frac": round((raw + comp) / (enc_ms / args.steps * 1e-3) / 1e9 / hbm, 4),
                 "decode_path_frac": round((raw + comp) / (dec_ms / args.steps * 1e-3) / 1e9 / hbm, 4)}
