@@ -151,6 +151,35 @@ def test_errors_through_the_abi(codec, oracle):
     assert np.array_equal(codec.decode(codec.encode(img)), img)  # context still healthy
 
 
+def test_corrupt_streams_never_crash(codec, oracle):
+    """Random damage anywhere in a stream — directory, length nibbles, row word counts, flat words, payload:
+    the decoder answers OK (garbage pixels) or FLIC_E_FORMAT, never faults, and the context stays usable.
+    Bounds come from validated header fields only, so no bit pattern can steer a load or store outside
+    the stream / the image."""
+    import flic_b200 as flic
+    rng = np.random.default_rng(77)
+    img = cases.gradient(384, 96, 4, 44)
+    good = codec.encode(img)
+    outcomes = {0: 0, -3: 0}
+    for trial in range(60):
+        bad = good.copy()
+        lo = 0 if trial % 3 else 32            # a third of the trials spare the file header
+        for _ in range(int(rng.integers(1, 12))):
+            i = int(rng.integers(lo, bad.size))
+            bad[i] ^= np.uint8(rng.integers(1, 256))
+        try:
+            out = codec.decode(bad)
+            assert out.shape == img.shape
+            outcomes[0] += 1
+        except flic.FlicError as e:
+            assert e.code == -3, e
+            outcomes[-3] += 1
+        rc = oracle.decode_rc(bad, img.shape)  # the CPU model must survive the same input
+        assert rc in (0, -3)
+    assert outcomes[0] and outcomes[-3]        # both outcomes occur, so the sweep is not vacuous
+    assert np.array_equal(codec.decode(good), img)
+
+
 def test_splice_of_gpu_parts(codec):
     """Block-row split: GPU-encoded halves splice into the GPU-encoded whole (the C4 multi-GPU path)."""
     import flic_b200 as flic
