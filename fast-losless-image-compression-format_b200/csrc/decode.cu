@@ -441,6 +441,9 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
         return;
     }
     const uint32_t *blk = sw + fixed + off;
+    if (pf) {  // pull the whole block (a few KB) towards L2 now: the LUT build below covers the DRAM latency
+        for (uint32_t i = 32u * lane; i < end - off; i += 32u * 32u) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
+    }
 
     ok = build_lut(lut, __ldg(blk + lane), lane);
 
