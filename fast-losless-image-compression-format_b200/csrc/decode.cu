@@ -119,117 +119,112 @@ __device__ __forceinline__ uint32_t get(BitReader &r, const char *luts, uint32_t
     return e;
 }
 
-__device__ __forceinline__ uint64_t shfl_up64d(uint64_t v, int d) {
-    uint32_t lo = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)v, d);
-    uint32_t hi = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), d);
-    return ((uint64_t)hi << 32) | lo;
-}
-__device__ __forceinline__ uint32_t cntd_get(uint64_t a, uint64_t b, uint32_t l) {
-    return (uint32_t)((l <= 6 ? a >> (9 * (l - 1)) : b >> (9 * (l - 7))) & 511u);
-}
-__device__ __forceinline__ void cntd_add(uint64_t &a, uint64_t &b, uint32_t l) {
-    if (l >= 1 && l <= 6) a += 1ull << (9 * (l - 1));
-    else if (l >= 7 && l <= 12) b += 1ull << (9 * (l - 7));
-}
+// Per-warp scratch of the LUT build.
+struct LutScratch {
+    uint16_t ent[256 + 2];  // LUT entries in canonical (length, symbol) order, then an all-zero terminator
+    uint32_t starts[32];    // bit v set: a code's span begins at LUT index v
+    uint32_t cnt[16];       // symbols per code length (running during the rank rounds)
+    uint32_t base[16];      // first LUT index of each length class
+    uint32_t below[16];     // symbols with a shorter code
+};
 
-// Builds the warp's LUT from the block's 32 nibble words. Returns false on a malformed table.
-__device__ bool build_lut(uint16_t *lut, uint32_t nibw, int lane) {
-    {   // entries not covered by any code decode as (symbol 0, 0 bits): loops stay bounded
-        uint4 z = make_uint4(0, 0, 0, 0);
-        uint4 *l4 = reinterpret_cast<uint4 *>(lut);
-        for (int i = lane; i < kLutSize * 2 / 16; i += 32) l4[i] = z;
-    }
-    uint32_t l8[8];
-    uint64_t ca = 0, cb = 0;
+// Builds the warp's LUT (2^kL entries of  len | symbol << 8) from the block's 32 nibble words.
+// Returns false on a malformed table.
+//
+// Canonical codes ordered by (length, symbol) tile the LUT with one contiguous span per symbol.  Eight
+// rounds give every symbol its rank within its length class (round r: lane L holds symbol 32r + L, the
+// lanes of equal length find each other with MATCH.ANY, a per-length running count lives in shared
+// memory); a scan over the ten lengths gives each class's first index; every symbol then drops its
+// entry at its canonical rank and sets the bit of its span's first index.  Finally each lane fills its
+// own 32 consecutive LUT entries — "how many spans have started up to here" is a popcount of the start
+// bits — with four 16-byte stores: no loops whose trip counts depend on the code, no conflicts.
+__device__ bool build_lut(uint16_t *lut, LutScratch &sc, uint32_t nibw, int lane) {
+    if (lane < 16) { sc.cnt[lane] = 0; }
+    sc.starts[lane] = 0;
+    __syncwarp();
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t len[8], rank[8];
     bool bad = false;
     int sole = -1;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        l8[k] = (nibw >> (4 * k)) & 15u;
-        if (l8[k] == kLenSole) sole = 8 * lane + k;
-        else if (l8[k] > (uint32_t)kL) bad = true;
-        cntd_add(ca, cb, l8[k]);
+    for (int r = 0; r < 8; ++r) {  // symbol 32r + lane: nibble (lane & 7) of word 4r + (lane >> 3)
+        const uint32_t w = __shfl_sync(0xFFFFFFFFu, nibw, 4 * r + (lane >> 3));
+        const uint32_t l = (w >> (4 * (lane & 7))) & 15u;
+        len[r] = l;
+        if (l == kLenSole) sole = 32 * r + lane;
+        else if (l > (uint32_t)kL) bad = true;
+        const uint32_t m = __match_any_sync(0xFFFFFFFFu, l);
+        const uint32_t before = sc.cnt[l];
+        rank[r] = before + __popc(m & lt);
+        __syncwarp();
+        if ((m & lt) == 0) sc.cnt[l] = before + __popc(m);  // the group's first lane
+        __syncwarp();
     }
-    uint64_t ia = ca, ib = cb;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint64_t ta = shfl_up64d(ia, d), tb = shfl_up64d(ib, d);
-        if (lane >= d) { ia += ta; ib += tb; }
-    }
-    uint64_t ea = ia - ca, eb = ib - cb;
-    // totals per length live in lane 31's inclusive counters
-    uint64_t ta, tb;
-    {
-        uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)ia, 31), hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(ia >> 32), 31);
-        ta = ((uint64_t)hi << 32) | lo;
-        lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)ib, 31); hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(ib >> 32), 31);
-        tb = ((uint64_t)hi << 32) | lo;
-    }
-    __syncwarp();
-
-    uint32_t solem = __ballot_sync(0xFFFFFFFFu, sole >= 0);
+    const uint32_t solem = __ballot_sync(0xFFFFFFFFu, sole >= 0);
     if (solem) {
         // one symbol, zero-length code: every LUT entry yields it and consumes nothing
-        uint32_t sym = (uint32_t)__shfl_sync(0xFFFFFFFFu, sole, __ffs(solem) - 1);
-        uint32_t *l32 = reinterpret_cast<uint32_t *>(lut);
-        for (int i = lane; i < kLutSize / 2; i += 32) l32[i] = (sym << 8) | (sym << 24);
+        const uint32_t sym = (uint32_t)__shfl_sync(0xFFFFFFFFu, sole, __ffs(solem) - 1);
+        uint4 *l4 = reinterpret_cast<uint4 *>(lut);
+        const uint32_t e2 = (sym << 8) | (sym << 24);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l4[4 * lane + i] = make_uint4(e2, e2, e2, e2);
         __syncwarp();
         return !__any_sync(0xFFFFFFFFu, bad);
     }
-
-    // first canonical code of each length, computed redundantly in registers
-    uint32_t start[8], span[8], ent[8];
+    // length classes: lane l (1..kL) owns class l
     {
-        uint32_t next = 0, prevnum = 0;
-        uint32_t nextl[kL + 1];
-        nextl[0] = 0;
+        const uint32_t n = (lane >= 1 && lane <= kL) ? sc.cnt[lane] : 0u;
+        const uint32_t span = n << ((kL - lane) & 31);
+        uint32_t is = span, in = n;
 #pragma unroll
-        for (int l = 1; l <= kL; ++l) {
-            next = (next + prevnum) << 1;
-            nextl[l] = next;
-            prevnum = cntd_get(ta, tb, l);
+        for (int d = 1; d < 16; d <<= 1) {
+            const uint32_t ts = __shfl_up_sync(0xFFFFFFFFu, is, d), tn = __shfl_up_sync(0xFFFFFFFFu, in, d);
+            if (lane >= d) { is += ts; in += tn; }
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint32_t l = l8[k];
-            start[k] = 0; span[k] = 0; ent[k] = 0;
-            if (l >= 1 && l <= (uint32_t)kL) {
-                uint32_t nl = 0;
-#pragma unroll
-                for (int t = 1; t <= kL; ++t)
-                    if ((uint32_t)t == l) nl = nextl[t];
-                uint32_t code = nl + cntd_get(ea, eb, l);
-                cntd_add(ea, eb, l);
-                start[k] = code << (kL - l);
-                span[k] = 1u << (kL - l);
-                ent[k] = ((uint32_t)(8 * lane + k) << 8) | l;
-                if (start[k] + span[k] > (uint32_t)kLutSize) { bad = true; span[k] = 0; }
-            }
-        }
-    }
-    // long codes (span <= 16 entries): the owning lane fills them
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (span[k] >= 1 && span[k] <= 16) {
-            for (uint32_t i = 0; i < span[k]; ++i) lut[start[k] + i] = (uint16_t)ent[k];
-        }
-    }
-    // short codes (span >= 32): the whole warp fills each span with 32-bit stores
-    uint32_t *l32 = reinterpret_cast<uint32_t *>(lut);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t m = __ballot_sync(0xFFFFFFFFu, span[k] >= 32);
-        while (m) {
-            int src = __ffs(m) - 1;
-            m &= m - 1;
-            uint32_t st = __shfl_sync(0xFFFFFFFFu, start[k], src);
-            uint32_t sp = __shfl_sync(0xFFFFFFFFu, span[k], src);
-            uint32_t en = __shfl_sync(0xFFFFFFFFu, ent[k], src);
-            for (uint32_t i = lane; i < sp / 2; i += 32) l32[st / 2 + i] = en | (en << 16);
+        if (lane < 16) { sc.base[lane] = is - span; sc.below[lane] = in - n; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, is, kL), nsym = __shfl_sync(0xFFFFFFFFu, in, kL);
+        if (total > (uint32_t)kLutSize) bad = true;  // over-subscribed lengths
+        if (lane == 0) {
+            sc.ent[nsym] = 0;  // terminator: indices past the last span decode as (symbol 0, 0 bits)
+            if (total < (uint32_t)kLutSize) sc.starts[total >> 5] = 1u << (total & 31);
         }
     }
     __syncwarp();
-    return !__any_sync(0xFFFFFFFFu, bad);
+    if (__any_sync(0xFFFFFFFFu, bad)) return false;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t l = len[r];
+        if (l) {
+            const uint32_t start = sc.base[l] + (rank[r] << (kL - l));
+            sc.ent[sc.below[l] + rank[r]] = (uint16_t)(l | ((uint32_t)(32 * r + lane) << 8));
+            atomicOr(&sc.starts[start >> 5], 1u << (start & 31));
+        }
+    }
+    __syncwarp();
+    // lane L fills LUT entries 32L .. 32L+31
+    const uint32_t flags = sc.starts[lane];
+    uint32_t upto = __popc(flags);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, upto, d);
+        if (lane >= d) upto += t;
+    }
+    const uint32_t first = upto - __popc(flags) - 1u;  // index of the span covering entry 32L - 1 (or -1)
+    uint4 *l4 = reinterpret_cast<uint4 *>(lut) + 4 * lane;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = 8 * q + 2 * j;
+            const uint32_t e0 = sc.ent[first + __popc(flags & ((2u << i) - 1u))];
+            const uint32_t e1 = sc.ent[first + __popc(flags & (i + 1 == 31 ? 0xFFFFFFFFu : ((2u << (i + 1)) - 1u)))];
+            w[j] = e0 | (e1 << 16);
+        }
+        l4[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncwarp();
+    return true;
 }
 
 // ---- per-lane pixel reconstruction ------------------------------------------------------------
@@ -417,6 +412,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
                                                           const unsigned long long *__restrict__ offsets, Geo g,
                                                           uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048, uint32_t pf) {
     __shared__ __align__(16) uint16_t luts[kDecWarps][kLutSize];
+    __shared__ LutScratch scratch[kDecWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t gb = (uint64_t)blockIdx.x * kDecWarps + warp;
     if (gb >= (uint64_t)g.n * g.nb) return;
@@ -445,7 +441,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
         for (uint32_t i = 32u * lane; i < end - off; i += 32u * 32u) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
     }
 
-    ok = build_lut(lut, __ldg(blk + lane), lane);
+    ok = build_lut(lut, scratch[warp], __ldg(blk + lane), lane);
 
     const bool active = lane < (int)p.bha;
     uint32_t rc = (__ldg(blk + 32 + (lane >> 1)) >> (16 * (lane & 1))) & 0xFFFFu;
