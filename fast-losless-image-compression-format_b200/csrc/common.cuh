@@ -41,10 +41,11 @@ struct BlockPos {
     uint32_t img, b, x0, y0, bwa, bha, rb;  // rb = bytes per block row = bwa * c
 };
 
-__device__ __forceinline__ BlockPos block_pos(const Geo &g, uint64_t gb) {
+__device__ __forceinline__ BlockPos block_pos(const Geo &g, uint64_t gb64) {
     BlockPos p;
-    p.img = (uint32_t)(gb / g.nb);
-    p.b = (uint32_t)(gb - (uint64_t)p.img * g.nb);
+    const uint32_t gb = (uint32_t)gb64;  // make_geo() keeps n * nb below 2^31: 32-bit divisions
+    p.img = gb / g.nb;
+    p.b = gb - p.img * g.nb;
     uint32_t by = p.b / g.nbx, bx = p.b - by * g.nbx;
     p.x0 = bx * kBW;
     p.y0 = by * kBH;
