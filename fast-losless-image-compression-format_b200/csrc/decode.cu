@@ -19,6 +19,10 @@ namespace flic {
 constexpr int kDecWarps = 4;
 // stream lines are pulled into L1 this many chunks of average consumption ahead (measured: 0 -> 2 is -7 %)
 constexpr uint32_t kPrefetchChunks = 2;
+// ... and the head of a block is pulled towards L2 while its LUT is built.  2 KB: more (the whole block)
+// gets evicted by the output stream before it is used and is read from DRAM twice (measured: DRAM reads
+// 0.96 GB with 0-2 KB, 1.06 GB with 4 KB, 1.46 GB with the whole block; time best at 2 KB)
+constexpr uint32_t kPrefetchL2Words = 512;
 // a one-word refill guarantees 32 buffered bits: that is floor(32 / kL) whole symbols
 constexpr int kSymsPerRefill = 32 / kL;
 
@@ -410,7 +414,7 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
 
 __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *__restrict__ streams,
                                                           const unsigned long long *__restrict__ offsets, Geo g,
-                                                          uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048, uint32_t pf) {
+                                                          uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048, uint32_t pf, uint32_t pf2) {
     __shared__ __align__(16) uint16_t luts[kDecWarps][kLutSize];
     __shared__ LutScratch scratch[kDecWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -437,8 +441,9 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
         return;
     }
     const uint32_t *blk = sw + fixed + off;
-    if (pf) {  // pull the whole block (a few KB) towards L2 now: the LUT build below covers the DRAM latency
-        for (uint32_t i = 32u * lane; i < end - off; i += 32u * 32u) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
+    if (pf2) {  // pull the block's head towards L2 now: the LUT build below covers the DRAM latency
+        const uint32_t lim = min(end - off, pf2);
+        for (uint32_t i = 32u * lane; i < lim; i += 32u * 32u) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
     }
 
     ok = build_lut(lut, scratch[warp], __ldg(blk + lane), lane);
@@ -492,7 +497,7 @@ void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offset
                    uint8_t *d_pixels, uint32_t *d_err, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
     unsigned grid = (unsigned)((total + kDecWarps - 1) / kDecWarps);
-    k_decode<<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks);
+    k_decode<<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words);
 }
 
 }  // namespace flic
