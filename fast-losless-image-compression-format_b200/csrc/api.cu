@@ -8,6 +8,8 @@
 #include <new>
 #include <vector>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 using namespace flic;
@@ -233,6 +235,30 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
     return FLIC_OK;
 }
 
+// TMA descriptor of a tightly packed RGBA pixel batch for k_decode's store path: 3-D {row bytes, rows,
+// images}, 64 B x 32 rows boxes, 64 B swizzle.  Returns false when the layout does not qualify (then the
+// kernel stores directly) or the driver entry point is missing.
+static bool make_pixel_map(const Geo &g, uint8_t *d_pixels, CUtensorMap *tm) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (encode_fn)fn;
+    }();
+    static const bool off = getenv("FLIC_NO_TMA") != nullptr;
+    if (off || !encode || g.c != 4 || !g.aligned16) return false;
+    const cuuint64_t dims[3] = {g.pitch, g.h, g.n};
+    const cuuint64_t strides[2] = {g.pitch, g.img_stride};
+    const cuuint32_t box[3] = {64, (cuuint32_t)kBH, 1}, estr[3] = {1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pixels, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams, const uint64_t *d_offsets, uint32_t n,
                                         uint32_t w, uint32_t h, uint32_t c, uint32_t flags, uint8_t *d_pixels,
                                         void *stream) {
@@ -242,8 +268,10 @@ extern "C" int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams,
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     { KernelTimer t(ctx, FLIC_K_DECODE, (cudaStream_t)stream);
+      alignas(64) CUtensorMap tm;
+      const bool tma = make_pixel_map(g, d_pixels, &tm);
       launch_decode((const uint32_t *)d_streams, (const unsigned long long *)d_offsets, g, d_pixels, ctx->d_err,
-                    (cudaStream_t)stream); }
+                    tma ? &tm : nullptr, (cudaStream_t)stream); }
     ctx->launches += 1;
     CU(cudaGetLastError());
     return FLIC_OK;

@@ -188,7 +188,8 @@ void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table,
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,
                      uint64_t capacity_words, unsigned long long *d_offsets, uint32_t *d_err,
                      cudaStream_t s);
+// tensor_map: a 128-byte CUtensorMap over the pixel buffer (api.cu: make_pixel_map), or nullptr
 void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offsets, const Geo &g,
-                   uint8_t *d_pixels, uint32_t *d_err, cudaStream_t s);
+                   uint8_t *d_pixels, uint32_t *d_err, const void *tensor_map, cudaStream_t s);
 
 }  // namespace flic

@@ -12,6 +12,10 @@
 // rows, done as a warp scan.
 //
 // Format: DESIGN.md §FLP0 (provisional; not the reference's bitstream).
+#include <cstring>
+
+#include <cuda.h>  // CUtensorMap (type only; the driver entry point is resolved in api.cu)
+
 #include "common.cuh"
 
 namespace flic {
@@ -328,9 +332,49 @@ __device__ __forceinline__ void acc_set(Acc &v, int ch, uint32_t val) {
 
 // FM >= 0: the block's flat mask is the compile-time FM (0, or 8 = opaque-alpha RGBA), rows run in unrolled
 // chunks.  FM < 0: any other mask, taken from `fmask` at run time — a plain per-pixel loop (rare blocks).
+// ---- TMA store path (RGBA, 16-byte-aligned images) ----------------------------------------------
+// A lane's 32 B stores each touch their own 128 B line, so a warp-wide store costs the LSU data pipe 32
+// wavefronts for 1 KB — and that pipe is what bounds this kernel.  Instead two chunks (16 pixels = 64 B
+// per row) are staged in shared memory with conflict-free 16 B stores (4 wavefronts each) and one thread
+// hands the 32 x 64 B tile to the TMA unit (cp.async.bulk.tensor, 3-D map {row bytes, rows, images}, so
+// tiles clip at the image's right and bottom edges).  The tile uses the 64 B swizzle: 16 B chunk c of row
+// r sits at chunk c ^ ((r >> 1) & 3).  Register budget: the loop only carries the tile's shared address
+// (0 = path off); the tile's origin and the descriptor address sit in a record right behind the tile and
+// are read by lane 0 per flush.
+constexpr uint32_t kTileBytes = 2048, kTileStride = kTileBytes + 512;  // 512 B keeps the swizzle phase of the next tile
+struct TileRec { unsigned long long map; uint32_t x0b, y0, img, pad; };
+__device__ __forceinline__ void tile_put(uint32_t tile, int lane, int half, const uint32_t *o) {
+    const uint32_t row = tile + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const uint32_t a = row + ((((uint32_t)(2 * half + c)) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(o[4 * c]), "r"(o[4 * c + 1]), "r"(o[4 * c + 2]),
+                     "r"(o[4 * c + 3]) : "memory");
+    }
+}
+__device__ __forceinline__ void tile_flush(uint32_t tile, int lane, uint32_t xbyte) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0) {
+        unsigned long long map;
+        uint32_t x0b, y0, img;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(map) : "r"(tile + kTileBytes));
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x0b), "=r"(y0) : "r"(tile + kTileBytes + 8));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(img) : "r"(tile + kTileBytes + 16));
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
+                     "r"(x0b + xbyte), "r"(y0), "r"(img), "r"(tile) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+__device__ __forceinline__ void tile_wait(int lane) {  // the tile may be overwritten once the TMA unit has read it
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+}
+
 template <int C, bool SG, int FM>
 __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel, uint32_t m2048, uint8_t *dst, int bwa,
-                            bool active, int aligned, int lane, uint32_t fmask, uint32_t fvals, uint32_t pfx) {
+                            bool active, int aligned, int lane, uint32_t fmask, uint32_t fvals, uint32_t pfx,
+                            uint32_t tma /* the warp's tile, or 0 */) {
     constexpr int FMC = FM < 0 ? 0 : FM;
     constexpr int U = Chunk<C, FMC>::U, W = Chunk<C, FMC>::W;
     const uint32_t amask = __ballot_sync(0xFFFFFFFFu, active);
@@ -385,7 +429,11 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
             else
                 decode_chunk<C, SG, FMC, false>(br, rs, acc, luts, wsel, m2048, o);
             uint8_t *d = dst + (size_t)x * C;
-            if (W == 8 && aligned == 2) {  // one 256-bit store: a whole 32-byte sector per lane and half the LSU wavefronts
+            const int half = (x >> 3) & 1;
+            if (C == 4 && tma && (half == 1 || x + 2 * U <= bwa)) {  // chunk pairs go out as one TMA tile
+                if (half == 0) { if (x > 0) tile_wait(lane); tile_put(tma, lane, 0, o); }
+                else { tile_put(tma, lane, 1, o); tile_flush(tma, lane, (uint32_t)(x - U) * 4u); }
+            } else if (W == 8 && aligned == 2) {  // one 256-bit store: a whole 32-byte sector per lane and half the LSU wavefronts
                 asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]),
                              "r"(o[3]), "r"(o[4 % W]), "r"(o[5 % W]), "r"(o[6 % W]), "r"(o[7 % W])
                              : "memory");
@@ -399,6 +447,7 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
             }
         }
     }
+    if (C == 4 && tma && FM >= 0) tile_wait(lane);  // the tile must outlive the TMA unit's read of it
     // ragged right edge of the image, and whole rows of blocks with an uncommon flat mask
     for (; x < bwa; ++x) {
 #pragma unroll
@@ -414,7 +463,9 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
 
 __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *__restrict__ streams,
                                                           const unsigned long long *__restrict__ offsets, Geo g,
-                                                          uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048, uint32_t pf, uint32_t pf2) {
+                                                          uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048, uint32_t pf, uint32_t pf2,
+                                                          const __grid_constant__ CUtensorMap tmap, uint32_t use_tma) {
+    __shared__ __align__(1024) uint8_t tiles[kDecWarps][kTileStride];  // TMA store staging, 32 rows x 64 B per warp (+ record)
     __shared__ __align__(16) uint16_t luts[kDecWarps][kLutSize];
     __shared__ LutScratch scratch[kDecWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -469,10 +520,20 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
                    (uint64_t)p.x0 * g.c;
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) != 0 && g.c >= 3;
     const int aligned = g.aligned16 ? (g.aligned32 ? 2 : 1) : 0;  // 0: byte stores, 1: 16-byte, 2: 32-byte
+    uint32_t tp = 0;
+    if (use_tma && g.c == 4) {
+        tp = (uint32_t)__cvta_generic_to_shared(&tiles[warp][0]);
+        if (lane == 0) {
+            TileRec *rec = reinterpret_cast<TileRec *>(&tiles[warp][kTileBytes]);
+            rec->map = reinterpret_cast<unsigned long long>(&tmap);
+            rec->x0b = p.x0 * 4u; rec->y0 = p.y0; rec->img = p.img;
+        }
+        __syncwarp();
+    }
     const char *lb = reinterpret_cast<const char *>(&luts[0][0]);
     const uint32_t wsel = (uint32_t)warp << 11;
     static_assert(kLutSize * 2 == 2048, "wsel assumes 2 KB per warp LUT");
-#define FLIC_ROWS(C, SG, FM) decode_rows<C, SG, FM>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane, fmask, fvals, pf)
+#define FLIC_ROWS(C, SG, FM) decode_rows<C, SG, FM>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane, fmask, fvals, pf, tp)
     if (fmask == 0) {
         switch (g.c) {
             case 1: FLIC_ROWS(1, false, 0); break;
@@ -494,10 +555,13 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
 }
 
 void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offsets, const Geo &g,
-                   uint8_t *d_pixels, uint32_t *d_err, cudaStream_t s) {
+                   uint8_t *d_pixels, uint32_t *d_err, const void *tensor_map, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
     unsigned grid = (unsigned)((total + kDecWarps - 1) / kDecWarps);
-    k_decode<<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words);
+    CUtensorMap tm;
+    if (tensor_map) memcpy(&tm, tensor_map, sizeof tm); else memset(&tm, 0, sizeof tm);
+    k_decode<<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words, tm,
+                                             tensor_map ? 1u : 0u);
 }
 
 }  // namespace flic
