@@ -409,7 +409,10 @@ def main():
         ach = alg[dom] / (kernels[dom]["avg_ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
                 "frac": round(ach / hbm, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "note": "k_decode: LSU data pipe ~72 % busy (LUT reads), ALU pipe ~50 %; not HBM bound (profiles/r01s2_ncu_full_c2x8.txt)",
+                "note": {"k_pack": "k_pack: ALU pipe 68 %, LSU data pipe 67 %, issue 77 % — integer-pipe bound, not HBM bound",
+                         "k_decode": "k_decode: LSU data pipe 76 % busy (LUT reads with 3.4-way bank conflicts), issue 65 % — not HBM bound",
+                         "k_histograms": "k_histograms: ~70 % of measured HBM peak with the residual plane (2N bytes of traffic)"}.get(dom, "")
+                        + " (profiles/r01s2_ncu_full_c2x8.txt)",
                 "algorithmic_bytes_per_launch": alg[dom],
                 "encode_path_frac": round((raw + comp) / (enc_ms / args.steps * 1e-3) / 1e9 / hbm, 4),
                 "decode_path_frac": round((raw + comp) / (dec_ms / args.steps * 1e-3) / 1e9 / hbm, 4)}
