@@ -371,7 +371,7 @@ __device__ __forceinline__ void tile_wait(int lane) {  // the tile may be overwr
     __syncwarp();
 }
 
-template <int C, bool SG, int FM>
+template <int C, bool SG, int FM, bool kTma>
 __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel, uint32_t m2048, uint8_t *dst, int bwa,
                             bool active, int aligned, int lane, uint32_t fmask, uint32_t fvals, uint32_t pfx,
                             uint32_t tma /* the warp's tile, or 0 */) {
@@ -430,7 +430,7 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
                 decode_chunk<C, SG, FMC, false>(br, rs, acc, luts, wsel, m2048, o);
             uint8_t *d = dst + (size_t)x * C;
             const int half = (x >> 3) & 1;
-            if (C == 4 && tma && (half == 1 || x + 2 * U <= bwa)) {  // chunk pairs go out as one TMA tile
+            if (kTma && C == 4 && tma && (half == 1 || x + 2 * U <= bwa)) {  // chunk pairs go out as one TMA tile
                 if (half == 0) { if (x > 0) tile_wait(lane); tile_put(tma, lane, 0, o); }
                 else { tile_put(tma, lane, 1, o); tile_flush(tma, lane, (uint32_t)(x - U) * 4u); }
             } else if (W == 8 && aligned == 2) {  // one 256-bit store: a whole 32-byte sector per lane and half the LSU wavefronts
@@ -447,7 +447,7 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
             }
         }
     }
-    if (C == 4 && tma && FM >= 0) tile_wait(lane);  // the tile must outlive the TMA unit's read of it
+    if (kTma && C == 4 && tma && FM >= 0) tile_wait(lane);  // the tile must outlive the TMA unit's read of it
     // ragged right edge of the image, and whole rows of blocks with an uncommon flat mask
     for (; x < bwa; ++x) {
 #pragma unroll
@@ -461,11 +461,14 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
     }
 }
 
+// kTma: the RGBA TMA-store variant; the plain variant carries none of that code (its other paths were
+// measurably slower with it compiled in).
+template <bool kTma>
 __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *__restrict__ streams,
                                                           const unsigned long long *__restrict__ offsets, Geo g,
                                                           uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048, uint32_t pf, uint32_t pf2,
-                                                          const __grid_constant__ CUtensorMap tmap, uint32_t use_tma) {
-    __shared__ __align__(1024) uint8_t tiles[kDecWarps][kTileStride];  // TMA store staging, 32 rows x 64 B per warp (+ record)
+                                                          const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(1024) uint8_t tiles[kTma ? kDecWarps : 1][kTma ? kTileStride : 16];  // TMA store staging, 32 rows x 64 B per warp (+ record)
     __shared__ __align__(16) uint16_t luts[kDecWarps][kLutSize];
     __shared__ LutScratch scratch[kDecWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) != 0 && g.c >= 3;
     const int aligned = g.aligned16 ? (g.aligned32 ? 2 : 1) : 0;  // 0: byte stores, 1: 16-byte, 2: 32-byte
     uint32_t tp = 0;
-    if (use_tma && g.c == 4) {
+    if (kTma && g.c == 4) {
         tp = (uint32_t)__cvta_generic_to_shared(&tiles[warp][0]);
         if (lane == 0) {
             TileRec *rec = reinterpret_cast<TileRec *>(&tiles[warp][kTileBytes]);
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
     const char *lb = reinterpret_cast<const char *>(&luts[0][0]);
     const uint32_t wsel = (uint32_t)warp << 11;
     static_assert(kLutSize * 2 == 2048, "wsel assumes 2 KB per warp LUT");
-#define FLIC_ROWS(C, SG, FM) decode_rows<C, SG, FM>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane, fmask, fvals, pf, tp)
+#define FLIC_ROWS(C, SG, FM) decode_rows<C, SG, FM, kTma>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane, fmask, fvals, pf, tp)
     if (fmask == 0) {
         switch (g.c) {
             case 1: FLIC_ROWS(1, false, 0); break;
@@ -560,8 +563,10 @@ void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offset
     unsigned grid = (unsigned)((total + kDecWarps - 1) / kDecWarps);
     CUtensorMap tm;
     if (tensor_map) memcpy(&tm, tensor_map, sizeof tm); else memset(&tm, 0, sizeof tm);
-    k_decode<<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words, tm,
-                                             tensor_map ? 1u : 0u);
+    if (tensor_map && g.c == 4)
+        k_decode<true><<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words, tm);
+    else
+        k_decode<false><<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words, tm);
 }
 
 }  // namespace flic
