@@ -3,13 +3,13 @@
 // One WARP per block, one LANE per row sub-stream (the format stores 32 word-
 // aligned row streams per block precisely so that a warp has 32 independent
 // bit-serial decodes in flight).  Per warp: read the 128-byte length table,
-// rebuild canonical codes with a packed-counter warp scan, fill a 2^kL-entry
-// shared-memory LUT (cooperatively for short codes, per lane for long ones),
-// exclusive-scan the row word counts into per-lane stream offsets, then every
-// lane runs a branch-light LUT decode with a 64-bit MSB-first bit buffer
-// (one refill per 32/kL symbols), undoes the left predictor in registers and
-// emits 16-byte vector stores.  Column 0 is a byte-wise prefix sum down the
-// rows, done as a warp scan.
+// rank the symbols within their length classes (MATCH.ANY rounds), fill the
+// 2^kL-entry shared-memory LUT (every lane its own 32 entries), exclusive-scan
+// the row word counts into per-lane stream offsets, then every lane runs a LUT
+// decode whose per-symbol work is shaped around the ALU pipe (see BitReader),
+// undoes the left predictor in 16-bit-lane running sums and hands RGBA pixels to
+// the TMA unit in 32 x 64 B tiles (other layouts: 256-/128-bit stores).  Column 0
+// is a byte-wise prefix sum down the rows, done as a warp scan.
 //
 // Format: DESIGN.md §FLP0 (provisional; not the reference's bitstream).
 #include <cstring>

@@ -1,16 +1,19 @@
-// encode.cu — the four encode kernels of the FLP0 engine (sm_100a).
+// encode.cu — the five encode kernels of the FLP0 engine (sm_100a).
 //
 //   k_histograms : one CTA per block; residuals computed in registers from
-//                  128-bit coalesced row loads, warp-privatised shared-memory
-//                  histograms, 512 B of u16 counts written per block.
-//   k_tables     : one WARP per block; bitonic sort of (count,symbol) keys,
-//                  two-queue Huffman merge, depth census, Kraft repair,
-//                  canonical code assignment by packed-counter warp scan.
-//   k_pack       : one CTA per block; residuals recomputed in registers (the
-//                  tile never touches shared memory), per-lane code
-//                  concatenation, warp scan of bit lengths, OR-scatter into a
-//                  shared staging tile, decoupled look-back over block sizes,
-//                  coalesced copy-out straight into the final stream position.
+//                  128-bit coalesced row loads and written to the residual
+//                  plane, warp-privatised shared-memory histograms, flat-channel
+//                  detection (FLP0 §2b), 512 B of u16 counts written per block.
+//   k_tables     : one WARP per 8 blocks; bitonic sort of (count,symbol) keys,
+//                  two-queue Huffman merge (one block per lane), depth census,
+//                  Kraft repair, canonical code assignment by packed-counter warp
+//                  scan, and the block's total of count x code length.
+//   k_slots      : exclusive prefix sum of block slot sizes (FLP0 §7): every
+//                  block's output position is known before anything is packed.
+//   k_pack       : one CTA per block; reads the residual plane, merges four
+//                  symbols into a code group, warp scan of bit lengths, RED.OR of
+//                  every group into a zeroed shared staging tile at its end bit
+//                  position, interleaving copy-out straight into the block's slot.
 //   k_finalize   : headers, rebased u32 directories and the n+1 stream offsets.
 //
 // Format: DESIGN.md §FLP0 (provisional; not the reference's bitstream —
