@@ -83,6 +83,24 @@ def test_batch_matches_per_image(codec, oracle):
     assert np.array_equal(codec.decode_batch(streams, off), imgs)
 
 
+def test_rgba_batch_ragged_edges(codec, oracle):
+    """RGBA batch whose blocks hang over the right and bottom image edges: the TMA store tiles of the
+    decoder must clip there (3-D tensor map: row bytes, rows, images) and never touch the next image."""
+    imgs = np.stack([cases.gradient(260, 70, 4, 200 + s) for s in range(5)])
+    imgs[1, ..., 3] = (np.arange(260)[None, :] % 256).astype(np.uint8)   # one image without a flat alpha
+    streams, off = codec.encode_batch(imgs)
+    for i in range(5):
+        assert np.array_equal(streams[int(off[i]): int(off[i + 1])], oracle.encode(imgs[i]))
+    guard = np.full((7, 70, 260, 4), 0xA5, dtype=np.uint8)
+    out = torch.from_numpy(guard).cuda()
+    d_s, d_o = dev(streams), torch.from_numpy(off.astype(np.int64)).cuda()
+    codec.decode_batch_device(d_s, d_o, out[1:6])
+    codec.check()
+    got = out.cpu().numpy()
+    assert np.array_equal(got[1:6], imgs)
+    assert (got[0] == 0xA5).all() and (got[6] == 0xA5).all()   # neighbours untouched
+
+
 def test_host_pipeline_many_chunks(codec, oracle, monkeypatch):
     """The host-buffer API streams the batch through double-buffered chunks; force 1-2 images per chunk
     so buffer reuse (chunk k vs k-2) and the offset rebasing are exercised, odd tail chunk included."""
@@ -149,6 +167,36 @@ def test_errors_through_the_abi(codec, oracle):
         codec.check()
     assert e.value.code == -2
     assert np.array_equal(codec.decode(codec.encode(img)), img)  # context still healthy
+
+
+def test_random_geometries(codec, oracle):
+    """Differential sweep: random sizes (ragged edges on both axes, widths that do and do not allow the
+    aligned / TMA store paths), channel counts, colour transform, flat and partly flat channels, smooth /
+    noisy / skewed content — GPU bytes == model bytes and both decoders return the pixels."""
+    rng = np.random.default_rng(2024)
+    for trial in range(120):
+        c = int(rng.integers(1, 5))
+        w = int(rng.choice([1, 7, 60, 127, 128, 129, 200, 255, 256, 260, 384, 500]))
+        h = int(rng.choice([1, 5, 31, 32, 33, 64, 70]))
+        kind = trial % 4
+        if kind == 0:
+            img = cases.gradient(w, h, c, 1000 + trial)
+        elif kind == 1:
+            img = cases.noise(w, h, c, 1000 + trial)
+        elif kind == 2:
+            img = cases.skewed(w, h, c, 1000 + trial)
+        else:
+            img = cases.gradient(w, h, c, 1000 + trial, sigma=float(rng.choice([0.0, 0.7, 12.0])))
+        if rng.random() < 0.4:                       # make some channels flat, everywhere or in the left part only
+            ch = int(rng.integers(0, c))
+            x1 = w if rng.random() < 0.5 else max(1, w // 2)
+            img = img.copy(); img[:, :x1, ch] = int(rng.integers(0, 256))
+        flags = 0x11 if (c >= 3 and rng.random() < 0.5) else 0x01
+        want = oracle.encode(img, flags)
+        got = codec.encode(img, flags)
+        assert np.array_equal(got, want), (trial, w, h, c, flags, kind)
+        assert np.array_equal(codec.decode(got), img), (trial, w, h, c, flags, kind)
+        assert np.array_equal(oracle.decode(got, img.shape), img), (trial, w, h, c, flags, kind)
 
 
 def test_corrupt_streams_never_crash(codec, oracle):
