@@ -30,6 +30,32 @@ def test_exports_match_header(flic):
     assert sorted(codec.EXPORTED) == names
 
 
+def test_header_is_plain_c_and_links(flic, tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 with no CUDA / C++ / torch types, and a C
+    caller must link against the library (link only — running it needs a GPU)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include "flic_b200.h"\n'
+        "int main(void) {\n"
+        "    flic_ctx *ctx = 0; flic_image_info info;\n"
+        "    unsigned char hdr[FLIC_HEADER_BYTES] = {0};\n"
+        "    if (flic_create(0, &ctx) != FLIC_OK) return flic_peek(hdr, sizeof hdr, &info) == FLIC_E_FORMAT ? 0 : 1;\n"
+        "    flic_destroy(ctx);\n"
+        "    return (int)(flic_max_stream_bytes(128, 32, 4) == 0);\n"
+        "}\n")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(flic.library_path())
+    exe = tmp_path / "caller"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{inc}", str(src), "-o", str(exe), f"-L{libdir}",
+                        "-lflicb200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_constants_agree_with_header(flic):
     text = open(os.path.join(ROOT, "include", "flic_b200.h")).read()
     d = dict(re.findall(r"#define (FLIC_[A-Z_]+) (\(?-?\w+\)?)", text))
