@@ -57,7 +57,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -335,7 +335,6 @@ def main():
         codec.decode_batch_device(streams, off, out, args.flags, st)
         b.record()
     barrier()
-    clocks = sampler.stop() if sampler else None
     launches = codec.launches - launches0
     codec.set_kernel_timing(False)
     ktimes = codec.kernel_times()
@@ -378,6 +377,7 @@ def main():
                "h2d_bytes_per_step": int(raw + nbytes + 8 * (n + 1)), "d2h_bytes_per_step": int(nbytes + raw + 8 * (n + 1) + 8),
                "note": "flic_encode_batch + flic_decode_batch on pinned host buffers; host wall clock, max over ranks"}
 
+    clocks = sampler.stop() if sampler else None  # sampled across warm-up, the device-timed steps and the e2e steps
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
