@@ -124,9 +124,16 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
         }
     }
     char *my = reinterpret_cast<char *>(sh[warp]);
+    uint32_t zero_rows = 0;  // RGBA rows whose alpha residuals are all zero (an opaque plane): counted, not looked up
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
-        if (nv[q] == 4 * C) {
+        if (C == 4 && __all_sync(0xFFFFFFFFu, nv[q] == 4 * C &&
+                                 ((res[q][0] | res[q][1 % C] | res[q][2 % C] | res[q][3 % C]) & 0xFF000000u) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4 * C; ++j)
+                if ((j & 3) != 3) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[q][j >> 2], j & 3)), 1u);
+            ++zero_rows;
+        } else if (nv[q] == 4 * C) {
 #pragma unroll
             for (int j = 0; j < 4 * C; ++j) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[q][j >> 2], j & 3)), 1u);
         } else if (nv[q] > 0) {
@@ -135,6 +142,7 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
                 if (j < nv[q]) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[q][j >> 2], j & 3)), 1u);
         }
     }
+    if (C == 4 && lane == 0 && zero_rows) atomicAdd(&sh[warp][0], zero_rows * (uint32_t)kBW);
     __syncthreads();
     uint32_t s = 0;
 #pragma unroll
