@@ -225,12 +225,17 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
     const uint64_t cap_words = capacity_bytes / 4;
     { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s); launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, ctx->d_flat, s); }
     { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, (uint64_t)n * g.nb, ctx->d_table, ctx->d_bits, s); }
-    { KernelTimer t(ctx, FLIC_K_SLOTS, s); launch_slots(g, ctx->d_bits, ctx->d_dirE, ctx->d_slot_status, ++ctx->slot_epoch, cap_words, ctx->d_err, s); }
+    bool fused;
+    { KernelTimer t(ctx, FLIC_K_SLOTS, s);
+      fused = launch_slots(g, ctx->d_bits, ctx->d_dirE, ctx->d_slot_status, ++ctx->slot_epoch, cap_words, ctx->d_err,
+                           (uint32_t *)d_streams, (unsigned long long *)d_offsets, s); }
+    if (!fused) {  // headers and directories depend on the slots only: before k_pack, off its tail
+        KernelTimer t(ctx, FLIC_K_FINALIZE, s);
+        launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s);
+    }
     { KernelTimer t(ctx, FLIC_K_PACK, s);
       launch_pack(ctx->d_resid, g, ctx->d_table, ctx->d_flat, (uint32_t *)d_streams, cap_words, ctx->d_dirE, ctx->d_err, s); }
-    { KernelTimer t(ctx, FLIC_K_FINALIZE, s);
-      launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s); }
-    ctx->launches += 5;
+    ctx->launches += fused ? 4 : 5;
     CU(cudaGetLastError());
     return FLIC_OK;
 }

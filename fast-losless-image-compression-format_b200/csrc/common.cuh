@@ -181,8 +181,9 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, uint2 *d_flat,
                        cudaStream_t s);
 void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s);
-void launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_dirE, unsigned long long *d_status,
-                  uint32_t epoch, uint64_t capacity_words, uint32_t *d_err, cudaStream_t s);
+bool launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_dirE, unsigned long long *d_status,
+                  uint32_t epoch, uint64_t capacity_words, uint32_t *d_err, uint32_t *d_streams,
+                  unsigned long long *d_offsets, cudaStream_t s);
 void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, const uint2 *d_flat, uint32_t *d_streams,
                  uint64_t capacity_words, const unsigned long long *d_dirE, uint32_t *d_err, cudaStream_t s);
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,

@@ -418,11 +418,56 @@ __global__ void __launch_bounds__(32) k_tables(const uint16_t *__restrict__ hist
 }
 
 void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s) {
-    // a few blocks per warp when that still fills the chip; kTabBpw (merge lanes busy) for large jobs
+    // one block per warp for small jobs (latency: 512x512 RGB 27 -> 21 us), a few when that still fills the
+    // chip, kTabBpw (merge lanes busy) for large jobs
     uint64_t want = nblocks / (148ull * 16);
-    int bpw = (int)(want < 2 ? 2 : (want > kTabBpw ? kTabBpw : want));
+    int bpw = (int)(want < 1 ? 1 : (want > kTabBpw ? kTabBpw : want));
     unsigned grid = (unsigned)((nblocks + bpw - 1) / bpw);
     k_tables<<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
+}
+
+// ------------------------------------------------------------------ k_finalize
+// Headers, rebased u32 directories and the n+1 stream offsets: all of it follows from dirE, so it needs
+// only k_slots' result (not k_pack's).  `first`/`stride` spread the items over whoever calls this.
+__device__ __forceinline__ void finalize_items(const Geo &g, const unsigned long long *dirE, uint32_t *streams,
+                                               uint64_t capacity_words, unsigned long long *offsets, uint64_t first_item,
+                                               uint64_t stride) {
+    const uint64_t per = kHdrWords + (uint64_t)g.nb + 1;  // header + directory words per image
+    const uint64_t items = (uint64_t)g.n * per;
+    for (uint64_t i = first_item; i < items + g.n + 1; i += stride) {
+        if (i >= items) {  // stream offsets in bytes
+            uint64_t img = i - items;
+            offsets[img] = 4ull * (img * per + dirE[img * g.nb]);
+            continue;
+        }
+        uint64_t img = i / per, k = i - img * per;
+        unsigned long long first = dirE[img * g.nb];
+        uint64_t pos = img * per + first + k;
+        if (pos >= capacity_words) continue;  // k_pack raises kErrCapacity
+        uint32_t v;
+        if (k >= kHdrWords) {
+            v = (uint32_t)(dirE[img * g.nb + (k - kHdrWords)] - first);
+        } else {
+            switch (k) {
+                case 0: v = kMagic; break;
+                case 1: v = kVersion | (g.c << 16) | ((g.flags & 0xFFu) << 24); break;
+                case 2: v = g.w; break;
+                case 3: v = g.h; break;
+                case 4: v = (uint32_t)kBW | ((uint32_t)kBH << 16); break;
+                case 5: v = g.nb; break;
+                case 6: v = (uint32_t)(dirE[(img + 1) * g.nb] - first); break;
+                default: v = (uint32_t)kL; break;
+            }
+        }
+        streams[pos] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_finalize(Geo g, const unsigned long long *__restrict__ dirE,
+                                                  uint32_t *__restrict__ streams, uint64_t capacity_words,
+                                                  unsigned long long *__restrict__ offsets) {
+    finalize_items(g, dirE, streams, capacity_words, offsets, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                   (uint64_t)gridDim.x * blockDim.x);
 }
 
 // ---------------------------------------------------------------------- k_slots
@@ -438,7 +483,8 @@ __device__ __forceinline__ uint32_t slot_words(uint32_t code_bits, uint32_t b, u
 __global__ void __launch_bounds__(kSlotThreads) k_slots(Geo g, const uint32_t *__restrict__ bits,
                                                         unsigned long long *__restrict__ dirE, uint32_t per,
                                                         uint32_t epoch, unsigned long long *status,
-                                                        uint64_t capacity_words, uint32_t *err) {
+                                                        uint64_t capacity_words, uint32_t *err, uint32_t *streams,
+                                                        unsigned long long *offsets) {
     __shared__ uint32_t wsum[32];
     __shared__ unsigned long long s_excl;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -493,16 +539,24 @@ __global__ void __launch_bounds__(kSlotThreads) k_slots(Geo g, const uint32_t *_
         dirE[total] = carry;
         if ((uint64_t)g.n * (kHdrWords + (uint64_t)g.nb + 1) + carry > capacity_words) atomicOr(err, kErrCapacity);
     }
+    if (gridDim.x == 1 && streams) {  // small job, one CTA: write the headers and directories here, save a launch
+        __syncthreads();
+        finalize_items(g, dirE, streams, capacity_words, offsets, tid, kSlotThreads);
+    }
 }
 
 // status: >= 128 u64, zeroed once at allocation; epoch: a value never used before on this status array (>= 1)
-void launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_dirE, unsigned long long *d_status,
-                  uint32_t epoch, uint64_t capacity_words, uint32_t *d_err, cudaStream_t s) {
+// Returns true when the (single) CTA also wrote headers and directories, i.e. k_finalize is not needed.
+bool launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_dirE, unsigned long long *d_status,
+                  uint32_t epoch, uint64_t capacity_words, uint32_t *d_err, uint32_t *d_streams,
+                  unsigned long long *d_offsets, cudaStream_t s) {
     const uint64_t total = (uint64_t)g.n * g.nb;
     uint64_t per = (total + 127) / 128;
     per = ((per < 2048 ? 2048 : per) + kSlotThreads - 1) / kSlotThreads * kSlotThreads;
     const unsigned grid = (unsigned)((total + per - 1) / per);  // <= 128: all CTAs are resident, the spin cannot deadlock
-    k_slots<<<grid, kSlotThreads, 0, s>>>(g, d_bits, d_dirE, (uint32_t)per, epoch, d_status, capacity_words, d_err);
+    k_slots<<<grid, kSlotThreads, 0, s>>>(g, d_bits, d_dirE, (uint32_t)per, epoch, d_status, capacity_words, d_err, d_streams,
+                                          d_offsets);
+    return grid == 1;
 }
 
 // ---------------------------------------------------------------------- k_pack
@@ -717,42 +771,6 @@ void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table,
         default: FLIC_PACK(4); break;
     }
 #undef FLIC_PACK
-}
-
-// ------------------------------------------------------------------ k_finalize
-__global__ void __launch_bounds__(256) k_finalize(Geo g, const unsigned long long *__restrict__ dirE,
-                                                  uint32_t *__restrict__ streams, uint64_t capacity_words,
-                                                  unsigned long long *__restrict__ offsets) {
-    const uint64_t per = kHdrWords + (uint64_t)g.nb + 1;  // header + directory words per image
-    const uint64_t items = (uint64_t)g.n * per;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < items + g.n + 1;
-         i += (uint64_t)gridDim.x * blockDim.x) {
-        if (i >= items) {  // stream offsets in bytes
-            uint64_t img = i - items;
-            offsets[img] = 4ull * (img * per + dirE[img * g.nb]);
-            continue;
-        }
-        uint64_t img = i / per, k = i - img * per;
-        unsigned long long first = dirE[img * g.nb];
-        uint64_t pos = img * per + first + k;
-        if (pos >= capacity_words) continue;  // k_pack already raised kErrCapacity
-        uint32_t v;
-        if (k >= kHdrWords) {
-            v = (uint32_t)(dirE[img * g.nb + (k - kHdrWords)] - first);
-        } else {
-            switch (k) {
-                case 0: v = kMagic; break;
-                case 1: v = kVersion | (g.c << 16) | ((g.flags & 0xFFu) << 24); break;
-                case 2: v = g.w; break;
-                case 3: v = g.h; break;
-                case 4: v = (uint32_t)kBW | ((uint32_t)kBH << 16); break;
-                case 5: v = g.nb; break;
-                case 6: v = (uint32_t)(dirE[(img + 1) * g.nb] - first); break;
-                default: v = (uint32_t)kL; break;
-            }
-        }
-        streams[pos] = v;
-    }
 }
 
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,
