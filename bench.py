@@ -265,6 +265,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2x64", choices=sorted(WORKLOADS))
     ap.add_argument("--flags", type=lambda s: int(s, 0), default=0x01)
+    ap.add_argument("--encoder", default="fused", choices=["fused", "staged"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--c4-height", type=int, default=0, help="override C4's 16384 rows (smoke runs)")
@@ -288,6 +289,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     flic_b200.build_library()
     codec = flic_b200.Codec(local)
+    codec.set_encoder(args.encoder)
 
     cfg, n = WORKLOADS[args.workload]
     # weak scaling: every rank owns its own `n` images (independent units, no data-path collective)
@@ -385,7 +387,8 @@ def main():
         return
 
     hbm, peak_src = peaks()
-    alg = {"k_histograms": raw, "k_tables": 0, "k_slots": 0, "k_pack": raw + comp, "k_finalize": 0, "k_decode": raw + comp}
+    alg = {"k_histograms": raw, "k_tables": 0, "k_slots": 0, "k_pack": raw + comp, "k_finalize": 0, "k_decode": raw + comp,
+           "k_encode": raw + comp, "k_decode_one": raw + comp}
     kernels = {}
     for k, (ms, cnt) in ktimes.items():
         if cnt:

@@ -13,8 +13,12 @@ from .build import build_library, library_path  # noqa: F401
 from .codec import (  # noqa: F401
     BLOCK_H,
     BLOCK_W,
+    FLAG_EXACT,
+    FLAG_ONE_STREAM,
     FLAG_SUBGREEN,
     MAX_CODE_LEN,
+    OP_DECODE,
+    OP_ENCODE,
     PRED_LEFT,
     Codec,
     FlicError,
@@ -22,5 +26,6 @@ from .codec import (  # noqa: F401
     max_stream_bytes,
     peek,
     splice_block_rows,
+    splice_plan,
 )
 from . import sharding, workloads  # noqa: F401

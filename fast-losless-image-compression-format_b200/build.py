@@ -4,8 +4,8 @@ import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SOURCES = ["csrc/encode.cu", "csrc/decode.cu", "csrc/api.cu"]
-_DEPS = _SOURCES + ["csrc/common.cuh", "../include/flic_b200.h"]
+_SOURCES = ["csrc/encode.cu", "csrc/decode.cu", "csrc/decode_one.cu", "csrc/splice.cu", "csrc/api.cu"]
+_DEPS = _SOURCES + ["csrc/common.cuh", "csrc/decode_common.cuh", "../include/flic_b200.h"]
 
 
 def library_path() -> str:

@@ -13,11 +13,14 @@ from .build import library_path
 
 BLOCK_W, BLOCK_H, MAX_CODE_LEN = 128, 32, 10
 PRED_LEFT, FLAG_SUBGREEN = 1, 0x10
+FLAG_ONE_STREAM, FLAG_EXACT = 0x20, 0x40   # optional stream layouts (include/flic_b200.h)
+OP_ENCODE, OP_DECODE = 0, 1
+ENCODER_FUSED, ENCODER_STAGED = 0, 1
 
 _ERR = {
     -1: "invalid argument", -2: "output buffer too small", -3: "malformed stream", -4: "CUDA error",
     -5: "no sm_100 CUDA device (there is no CPU fallback)", -6: "unsupported format feature",
-    -7: "device-side consistency check failed",
+    -7: "device-side consistency check failed", -8: "a submitted operation has not been waited for",
 }
 
 
@@ -65,6 +68,16 @@ def load_library():
         "flic_launch_count": (u64, [vp]),
         "flic_set_kernel_timing": (i32, [vp, i32]),
         "flic_get_kernel_times": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
+        "flic_set_option": (i32, [vp, i32, i32]),
+        "flic_host_register": (i32, [vp, u64]),
+        "flic_host_unregister": (i32, [vp]),
+        "flic_encode_submit": (i32, [vp, vp, u32, u32, u32, u32, u32, vp, u64, vp]),
+        "flic_decode_submit": (i32, [vp, vp, vp, u32, vp, u64]),
+        "flic_wait": (i32, [vp, i32]),
+        "flic_splice_block_rows_device": (i32, [vp, C.POINTER(vp), C.POINTER(u64), u32, vp, u64, C.POINTER(u64), vp]),
+        "flic_splice_plan": (i32, [C.POINTER(u32), C.POINTER(u32), u32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "flic_splice_finish_device": (i32, [vp, vp, C.POINTER(u32), C.POINTER(u32), u32, u32, u32, u32, u32, vp]),
+        "flic_split_finish_device": (i32, [vp, vp, u32, u32, u32, u32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -77,10 +90,12 @@ EXPORTED = (
     "flic_create flic_destroy flic_strerror flic_last_error flic_version flic_blocks_per_image "
     "flic_max_stream_bytes flic_encode_batch_device flic_decode_batch_device flic_check flic_encode_batch "
     "flic_decode_batch flic_peek flic_splice_block_rows flic_stage_histograms flic_stage_tables "
-    "flic_launch_count flic_set_kernel_timing flic_get_kernel_times"
+    "flic_launch_count flic_set_kernel_timing flic_get_kernel_times flic_set_option flic_host_register "
+    "flic_host_unregister flic_encode_submit flic_decode_submit flic_wait flic_splice_block_rows_device "
+    "flic_splice_plan flic_splice_finish_device flic_split_finish_device"
 ).split()
 
-KERNELS = ("k_histograms", "k_tables", "k_pack", "k_finalize", "k_decode", "k_slots")
+KERNELS = ("k_histograms", "k_tables", "k_pack", "k_finalize", "k_decode", "k_slots", "k_encode", "k_decode_one")
 
 
 def max_stream_bytes(w, h, c):
@@ -116,6 +131,19 @@ def splice_block_rows(parts):
     return out[: n.value].copy()
 
 
+def splice_plan(part_blocks, part_payload_words):
+    """Where each part's directory entries and payload land in the spliced stream (host arithmetic only).
+    Returns (dir_byte_offsets, payload_byte_offsets, total_bytes)."""
+    k = len(part_blocks)
+    nb = (C.c_uint32 * k)(*[int(x) for x in part_blocks])
+    pw = (C.c_uint32 * k)(*[int(x) for x in part_payload_words])
+    d, p, tot = (C.c_uint64 * k)(), (C.c_uint64 * k)(), C.c_uint64(0)
+    rc = load_library().flic_splice_plan(nb, pw, k, d, p, C.byref(tot))
+    if rc:
+        raise FlicError(rc)
+    return list(d), list(p), int(tot.value)
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
@@ -145,6 +173,38 @@ class Codec:
     @property
     def launches(self):
         return int(self.lib.flic_launch_count(self.h))
+
+    def set_encoder(self, which):
+        """'fused' (default: one pass over the pixels) or 'staged' (round-1 five-kernel pipeline; same bytes)."""
+        self._chk(self.lib.flic_set_option(self.h, 1, {"fused": ENCODER_FUSED, "staged": ENCODER_STAGED}[which]))
+
+    # ---- submit / wait: one encode and one decode may be in flight together ----
+    def encode_submit(self, pixels, flags=PRED_LEFT, out=None, offsets=None):
+        """Asynchronous encode_batch on caller-owned (ideally pinned) buffers; returns (out, offsets) to be read
+        after wait(OP_ENCODE)."""
+        px = pixels
+        if px.dtype != np.uint8 or not px.flags.c_contiguous or px.ndim != 4:
+            raise FlicError(-1, "pixels must be a C-contiguous uint8 [n,h,w,c] array that outlives the wait")
+        n, h, w, c = px.shape
+        if out is None:
+            out = np.empty(max(n * max_stream_bytes(w, h, c), 1), dtype=np.uint8)
+        if offsets is None:
+            offsets = np.zeros(n + 1, dtype=np.uint64)
+        self._keep_enc = (px, out, offsets)
+        self._chk(self.lib.flic_encode_submit(self.h, px.ctypes.data, n, w, h, c, flags, out.ctypes.data, out.size,
+                                              offsets.ctypes.data))
+        return out, offsets
+
+    def decode_submit(self, streams, offsets, out):
+        if streams.dtype != np.uint8 or offsets.dtype != np.uint64 or not out.flags.c_contiguous:
+            raise FlicError(-1, "streams uint8, offsets uint64, out C-contiguous; all must outlive the wait")
+        self._keep_dec = (streams, offsets, out)
+        self._chk(self.lib.flic_decode_submit(self.h, streams.ctypes.data, offsets.ctypes.data, offsets.size - 1,
+                                              out.ctypes.data, out.nbytes))
+        return out
+
+    def wait(self, op):
+        self._chk(self.lib.flic_wait(self.h, int(op)))
 
     # ---- host-buffer API: numpy in, numpy out; H2D/D2H inside the call ----
     def encode_batch(self, pixels, flags=PRED_LEFT, out=None, offsets=None):
@@ -196,6 +256,27 @@ class Codec:
 
     def check(self, stream=0):
         self._chk(self.lib.flic_check(self.h, C.c_void_p(stream)))
+
+    # ---- block-row splice on the device (torch CUDA uint8 tensors) ----
+    def splice_block_rows_device(self, parts, out, stream=0):
+        """parts: list of CUDA uint8 tensors, each one stream of a run of whole block rows; out: CUDA uint8 tensor.
+        Returns the number of bytes of the spliced stream written to out."""
+        k = len(parts)
+        ptrs = (C.c_void_p * k)(*[p.data_ptr() for p in parts])
+        sizes = (C.c_uint64 * k)(*[p.numel() for p in parts])
+        n = C.c_uint64(0)
+        self._chk(self.lib.flic_splice_block_rows_device(self.h, ptrs, sizes, k, _ptr(out), out.numel(), C.byref(n),
+                                                         C.c_void_p(stream)))
+        return int(n.value)
+
+    def splice_finish_device(self, out, part_blocks, part_payload_words, w, h_total, c, flags=PRED_LEFT, stream=0):
+        k = len(part_blocks)
+        nb = (C.c_uint32 * k)(*[int(x) for x in part_blocks])
+        pw = (C.c_uint32 * k)(*[int(x) for x in part_payload_words])
+        self._chk(self.lib.flic_splice_finish_device(self.h, _ptr(out), nb, pw, k, w, h_total, c, flags, C.c_void_p(stream)))
+
+    def split_finish_device(self, part, w, h_part, c, flags=PRED_LEFT, stream=0):
+        self._chk(self.lib.flic_split_finish_device(self.h, _ptr(part), w, h_part, c, flags, C.c_void_p(stream)))
 
     # ---- measurement hooks ----
     def set_kernel_timing(self, enable):

@@ -1,11 +1,15 @@
 // api.cu — C ABI of libflicb200.so (include/flic_b200.h): context, workspace,
-// device-resident and host-buffer batch entry points, header parsing and the
-// block-row splice.  Host logic only; every byte of codec work happens in the
-// kernels of encode.cu / decode.cu.  There is no CPU fallback anywhere here.
+// device-resident and host-buffer batch entry points (blocking and submit/wait),
+// header parsing and the block-row splice (host and device).  Host logic only; every
+// byte of codec work happens in the kernels of encode.cu / decode.cu / decode_one.cu.
+// There is no CPU fallback anywhere here.
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include <cuda.h>
@@ -14,30 +18,56 @@
 
 using namespace flic;
 
-struct flic_ctx {
-    int device = 0;
-    char msg[256] = {0};
-    uint64_t launches = 0;
-    // per-block workspace (grown on demand)
-    uint64_t ws_blocks = 0;
-    uint16_t *d_hist = nullptr, *d_table = nullptr;
-    uint32_t *d_resid = nullptr;  // residual plane: 32 rows x 32 lanes x C words (<= 16 KB) per block
-    uint2 *d_flat = nullptr;      // per block {flat-channel mask, values}
-    uint32_t *d_bits = nullptr;             // per block: sum of count x code length
-    unsigned long long *d_dirE = nullptr;   // per block: exclusive prefix sum of slot words (+ grand total)
-    unsigned long long *d_slot_status = nullptr;  // k_slots: 128 epoch-tagged run sums
-    uint32_t slot_epoch = 0;
-    uint32_t *d_err = nullptr;
-    uint32_t *h_err = nullptr;  // pinned
-    // host-API pipeline: chunks of the batch flow H2D -> kernels -> D2H on three streams with
-    // double-buffered device staging, so PCIe in, compute and PCIe out overlap (grown on demand)
+namespace {
+// Staging of one direction of the host-buffer API: chunks of the batch flow H2D -> kernels -> D2H on three
+// streams with double-buffered device buffers, so PCIe in, compute and PCIe out overlap.  Encode and decode
+// own separate pipes, so an encode call and a decode call (flic_*_submit) can be in flight together and use
+// both directions of the link at once.
+struct Pipe {
     uint8_t *d_pix[2] = {nullptr, nullptr}, *d_str[2] = {nullptr, nullptr};
     unsigned long long *d_off[2] = {nullptr, nullptr};
     unsigned long long *h_off[2] = {nullptr, nullptr};  // pinned, off_cap entries each
     uint64_t pix_cap = 0, str_cap = 0, off_cap = 0;
-    cudaStream_t stream = nullptr;                      // kernels of the host-buffer API
-    cudaStream_t s_in = nullptr, s_out = nullptr;       // H2D / D2H
+    cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;  // kernels / H2D / D2H
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    // submit/wait
+    std::thread worker;
+    bool busy = false;
+    int result = FLIC_OK;
+};
+}  // namespace
+
+struct flic_ctx {
+    int device = 0;
+    char msg[256] = {0};
+    std::atomic<uint64_t> launches{0};  // encode and decode workers (flic_*_submit) may both be launching
+    int encoder = FLIC_ENCODER_FUSED;
+    // per-block workspace (grown on demand)
+    uint64_t ws_blocks = 0;
+    bool ws_staged = false;       // the staged encoder's extra arrays are allocated
+    uint16_t *d_hist = nullptr, *d_table = nullptr;
+    uint32_t *d_resid = nullptr;  // staged encoder: residual plane, 32 rows x 32 lanes x C words (<= 16 KB) per block
+    uint2 *d_flat = nullptr;      // staged encoder: per block {flat-channel mask, values}
+    uint32_t *d_bits = nullptr;             // staged encoder: per block sum of count x code length
+    unsigned long long *d_dirE = nullptr;   // per block: exclusive prefix sum of block sizes in words (+ grand total)
+    unsigned long long *d_status = nullptr; // fused encoder: per block look-back status (epoch-tagged, never memset)
+    unsigned long long *d_ticket = nullptr; // fused encoder: block ticket counter (monotonic across launches)
+    unsigned long long ticket_base = 0;
+    uint32_t fused_epoch = 0;
+    unsigned long long *d_slot_status = nullptr;  // staged encoder, k_slots: 128 epoch-tagged run sums
+    uint32_t slot_epoch = 0;
+    int slots_max_grid = 0;       // co-resident k_slots CTAs on this device (occupancy API)
+    // the workspace is one per context: an encode on another stream first waits for the previous one
+    cudaEvent_t ev_ws = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
+    // device-side error flags: word 0 is raised by encode kernels, word 1 by decode kernels, so that an encode
+    // and a decode in flight together (flic_*_submit) each report their own.  h_err: four pinned words —
+    // [0] / [1] are read by the encode / decode pipelines, [2..3] by flic_check
+    uint32_t *d_err = nullptr;
+    uint32_t *h_err = nullptr;
+    std::mutex span_mu;
+    Pipe enc, dec;
     // opt-in per-kernel timing (flic_set_kernel_timing): event pairs recorded on the launching stream
     bool timing = false;
     struct Span { cudaEvent_t a, b; int kernel; };
@@ -51,7 +81,11 @@ struct KernelTimer {
     flic_ctx *ctx; cudaStream_t s; flic_ctx::Span sp; bool on;
     KernelTimer(flic_ctx *c, int kernel, cudaStream_t st) : ctx(c), s(st), on(c->timing) {
         if (!on) return;
-        if (!ctx->free_spans.empty()) { sp = ctx->free_spans.back(); ctx->free_spans.pop_back(); }
+        std::unique_lock<std::mutex> lk(ctx->span_mu);
+        const bool reuse = !ctx->free_spans.empty();
+        if (reuse) { sp = ctx->free_spans.back(); ctx->free_spans.pop_back(); }
+        lk.unlock();
+        if (reuse) {}
         else if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) { on = false; return; }
         sp.kernel = kernel;
         cudaEventRecord(sp.a, s);
@@ -59,6 +93,7 @@ struct KernelTimer {
     ~KernelTimer() {
         if (!on) return;
         cudaEventRecord(sp.b, s);
+        std::lock_guard<std::mutex> lk(ctx->span_mu);
         ctx->spans.push_back(sp);
     }
 };
@@ -74,7 +109,13 @@ static int cuda_fail(flic_ctx *ctx, cudaError_t e, const char *what) {
         if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);   \
     } while (0)
 
-static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+// overflow-safe ceil(a / b)
+static inline uint64_t cdiv(uint64_t a, uint64_t b) { return a / b + (a % b != 0); }
+
+static inline bool flags_ok(uint32_t flags) {
+    return (flags & 0x0Fu) == FLIC_PRED_LEFT && (flags & ~FLIC_FLAGS_ALL) == 0 &&
+           !((flags & FLIC_FLAG_ONE_STREAM) && (flags & FLIC_FLAG_EXACT));
+}
 
 extern "C" int flic_version(void) { return (int)kVersion; }
 
@@ -88,21 +129,46 @@ extern "C" const char *flic_strerror(int code) {
         case FLIC_E_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
         case FLIC_E_UNSUPPORTED: return "unsupported format feature";
         case FLIC_E_INTERNAL: return "device-side consistency check failed";
+        case FLIC_E_BUSY: return "an operation submitted on this context has not been waited for";
         default: return "unknown error";
     }
 }
 
 extern "C" const char *flic_last_error(const flic_ctx *ctx) { return ctx ? ctx->msg : ""; }
-extern "C" uint64_t flic_launch_count(const flic_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t flic_launch_count(const flic_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
-extern "C" uint64_t flic_blocks_per_image(uint32_t w, uint32_t h) {
-    return (uint64_t)cdiv(w, kBW) * cdiv(h, kBH);
-}
+extern "C" uint64_t flic_blocks_per_image(uint32_t w, uint32_t h) { return cdiv(w, kBW) * cdiv(h, kBH); }
 
 extern "C" uint64_t flic_max_stream_bytes(uint32_t w, uint32_t h, uint32_t c) {
     uint64_t nb = flic_blocks_per_image(w, h);
     uint64_t blk = kBlkHdrWords + (uint64_t)kBH * ((kBW * c * kL + 31) / 32 + 1);  // + slot slack: one word per row
     return 4ull * (kHdrWords + nb + 1 + nb * blk);
+}
+
+static cudaError_t pipe_create(Pipe &p) {
+    cudaError_t e = cudaStreamCreateWithFlags(&p.s_k, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&p.ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.ev_k[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.ev_out[i], cudaEventDisableTiming);
+    }
+    return e;
+}
+
+static void pipe_destroy(Pipe &p) {
+    if (p.worker.joinable()) p.worker.join();
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(p.d_pix[i]); cudaFree(p.d_str[i]); cudaFree(p.d_off[i]);
+        if (p.h_off[i]) cudaFreeHost(p.h_off[i]);
+        if (p.ev_in[i]) cudaEventDestroy(p.ev_in[i]);
+        if (p.ev_k[i]) cudaEventDestroy(p.ev_k[i]);
+        if (p.ev_out[i]) cudaEventDestroy(p.ev_out[i]);
+    }
+    if (p.s_k) cudaStreamDestroy(p.s_k);
+    if (p.s_in) cudaStreamDestroy(p.s_in);
+    if (p.s_out) cudaStreamDestroy(p.s_out);
 }
 
 extern "C" int flic_create(int device, flic_ctx **out) {
@@ -115,21 +181,20 @@ extern "C" int flic_create(int device, flic_ctx **out) {
     flic_ctx *ctx = new (std::nothrow) flic_ctx;
     if (!ctx) return FLIC_E_ARG;
     ctx->device = device;
+    if (const char *e = getenv("FLIC_ENCODER")) ctx->encoder = strcmp(e, "staged") == 0 ? FLIC_ENCODER_STAGED : FLIC_ENCODER_FUSED;
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_err, sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemset(ctx->d_err, 0, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_err, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_err, 0, 2 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_slot_status, 128 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_slot_status, 0, 128 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_err, sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
-    }
-    if (e != cudaSuccess) {
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ticket, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_ticket, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_err, 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_ws, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = pipe_create(ctx->enc);
+    if (e == cudaSuccess) e = pipe_create(ctx->dec);
+    if (e == cudaSuccess) ctx->slots_max_grid = slots_max_resident_ctas();
+    if (e != cudaSuccess || ctx->slots_max_grid < 1) {
         flic_destroy(ctx);
         return FLIC_E_CUDA;
     }
@@ -137,53 +202,73 @@ extern "C" int flic_create(int device, flic_ctx **out) {
     return FLIC_OK;
 }
 
+static void free_workspace(flic_ctx *ctx) {
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_bits); cudaFree(ctx->d_dirE);
+    cudaFree(ctx->d_resid); cudaFree(ctx->d_flat); cudaFree(ctx->d_status);
+    ctx->d_hist = ctx->d_table = nullptr; ctx->d_bits = nullptr; ctx->d_dirE = nullptr; ctx->d_resid = nullptr;
+    ctx->d_flat = nullptr; ctx->d_status = nullptr;
+    ctx->ws_blocks = 0; ctx->ws_staged = false;
+}
+
 extern "C" void flic_destroy(flic_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_bits); cudaFree(ctx->d_dirE);
-    cudaFree(ctx->d_resid); cudaFree(ctx->d_flat); cudaFree(ctx->d_err); cudaFree(ctx->d_slot_status);
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(ctx->d_pix[i]); cudaFree(ctx->d_str[i]); cudaFree(ctx->d_off[i]);
-        if (ctx->h_off[i]) cudaFreeHost(ctx->h_off[i]);
-        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
-        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
-        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
-    }
+    pipe_destroy(ctx->enc);
+    pipe_destroy(ctx->dec);
+    cudaDeviceSynchronize();
+    free_workspace(ctx);
+    cudaFree(ctx->d_err); cudaFree(ctx->d_slot_status); cudaFree(ctx->d_ticket);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
-    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->ev_ws) cudaEventDestroy(ctx->ev_ws);
     for (auto &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto &sp : ctx->free_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     delete ctx;
 }
 
-static int ensure_workspace(flic_ctx *ctx, uint64_t blocks) {
-    if (blocks <= ctx->ws_blocks) return FLIC_OK;
-    cudaFree(ctx->d_hist); cudaFree(ctx->d_table); cudaFree(ctx->d_bits); cudaFree(ctx->d_dirE);
-    cudaFree(ctx->d_resid); cudaFree(ctx->d_flat);
-    ctx->d_hist = ctx->d_table = nullptr; ctx->d_bits = nullptr; ctx->d_dirE = nullptr; ctx->d_resid = nullptr; ctx->d_flat = nullptr;
-    ctx->ws_blocks = 0;
-    CU(cudaMalloc(&ctx->d_resid, blocks * (uint64_t)kBH * 512));
-    CU(cudaMalloc(&ctx->d_flat, blocks * sizeof(uint2)));
-    CU(cudaMalloc(&ctx->d_hist, blocks * 256 * sizeof(uint16_t)));
-    CU(cudaMalloc(&ctx->d_table, blocks * 256 * sizeof(uint16_t)));
-    CU(cudaMalloc(&ctx->d_bits, blocks * sizeof(uint32_t)));
+extern "C" int flic_set_option(flic_ctx *ctx, int option, int value) {
+    if (!ctx) return FLIC_E_ARG;
+    switch (option) {
+        case FLIC_OPT_ENCODER:
+            if (value != FLIC_ENCODER_FUSED && value != FLIC_ENCODER_STAGED) return FLIC_E_ARG;
+            ctx->encoder = value;
+            return FLIC_OK;
+        default: return FLIC_E_ARG;
+    }
+}
+
+static int ensure_workspace(flic_ctx *ctx, uint64_t blocks, bool staged) {
+    if (blocks <= ctx->ws_blocks && (!staged || ctx->ws_staged)) return FLIC_OK;
+    CU(cudaDeviceSynchronize());  // nothing may still be using the arrays about to be freed
+    if (blocks < ctx->ws_blocks) blocks = ctx->ws_blocks;
+    staged = staged || ctx->ws_staged;
+    free_workspace(ctx);
     CU(cudaMalloc(&ctx->d_dirE, (blocks + 1) * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ctx->d_status, blocks * sizeof(unsigned long long)));
+    CU(cudaMemset(ctx->d_status, 0, blocks * sizeof(unsigned long long)));
+    ctx->fused_epoch = 0;
+    if (staged) {
+        CU(cudaMalloc(&ctx->d_resid, blocks * (uint64_t)kBH * 512));
+        CU(cudaMalloc(&ctx->d_flat, blocks * sizeof(uint2)));
+        CU(cudaMalloc(&ctx->d_hist, blocks * 256 * sizeof(uint16_t)));
+        CU(cudaMalloc(&ctx->d_table, blocks * 256 * sizeof(uint16_t)));
+        CU(cudaMalloc(&ctx->d_bits, blocks * sizeof(uint32_t)));
+    }
     ctx->ws_blocks = blocks;
+    ctx->ws_staged = staged;
     return FLIC_OK;
 }
 
 static int make_geo(const void *base, uint32_t n, uint32_t w, uint32_t h, uint32_t c, uint32_t flags, Geo *g) {
     if (n == 0 || w == 0 || h == 0 || c < 1 || c > 4) return FLIC_E_ARG;
-    if ((flags & 0x0Fu) != FLIC_PRED_LEFT || (flags & ~0x1Fu)) return FLIC_E_ARG;
+    if (!flags_ok(flags)) return FLIC_E_ARG;
+    const uint64_t nbx = cdiv(w, kBW), nby = cdiv(h, kBH), nb = nbx * nby;
+    if (nb > 0xFFFFFFFFull || (uint64_t)n * nb >= (1ull << 31)) return FLIC_E_ARG;  // kernels index blocks in 31 bits
     g->n = n; g->w = w; g->h = h; g->c = c; g->flags = flags;
-    g->nbx = cdiv(w, kBW); g->nby = cdiv(h, kBH); g->nb = g->nbx * g->nby;
+    g->nbx = (uint32_t)nbx; g->nby = (uint32_t)nby; g->nb = (uint32_t)nb;
     g->pitch = (uint64_t)w * c;
     g->img_stride = g->pitch * h;
     g->aligned16 = (((uintptr_t)base | g->pitch | g->img_stride) & 15u) == 0;
     g->aligned32 = (((uintptr_t)base | g->pitch | g->img_stride) & 31u) == 0;
-    if ((uint64_t)n * g->nb >= (1ull << 31)) return FLIC_E_ARG;
     return FLIC_OK;
 }
 
@@ -202,9 +287,11 @@ extern "C" int flic_stage_histograms(flic_ctx *ctx, const uint8_t *d_pixels, uin
 
 extern "C" int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t n_blocks_total, uint16_t *d_table,
                                  uint32_t *d_bits, void *stream) {
-    if (!ctx || !d_hist || !d_table || n_blocks_total == 0) return FLIC_E_ARG;
+    if (!ctx || !d_hist || !d_table || n_blocks_total == 0 || n_blocks_total >= (1ull << 31)) return FLIC_E_ARG;
     CU(cudaSetDevice(ctx->device));
-    { KernelTimer t(ctx, FLIC_K_TABLES, (cudaStream_t)stream); launch_tables(d_hist, n_blocks_total, d_table, d_bits, (cudaStream_t)stream); }
+    { KernelTimer t(ctx, FLIC_K_TABLES, (cudaStream_t)stream);
+      if (ctx->encoder == FLIC_ENCODER_FUSED) launch_tables_cta(d_hist, n_blocks_total, d_table, d_bits, (cudaStream_t)stream);  // the fused kernel's builder
+      else launch_tables(d_hist, n_blocks_total, d_table, d_bits, (cudaStream_t)stream); }
     ctx->launches += 1;
     CU(cudaGetLastError());
     return FLIC_OK;
@@ -218,32 +305,52 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
     int rc = make_geo(d_pixels, n, w, h, c, flags, &g);
     if (rc) return rc;
     if (capacity_bytes < 4ull * n * (kHdrWords + (uint64_t)g.nb + 1)) return FLIC_E_CAPACITY;
+    const bool staged = ctx->encoder == FLIC_ENCODER_STAGED && !(flags & (FLIC_FLAG_ONE_STREAM | FLIC_FLAG_EXACT));
     CU(cudaSetDevice(ctx->device));
-    rc = ensure_workspace(ctx, (uint64_t)n * g.nb);
+    rc = ensure_workspace(ctx, (uint64_t)n * g.nb, staged);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    if (ctx->ws_used && ctx->ws_stream != s) CU(cudaStreamWaitEvent(s, ctx->ev_ws, 0));  // one workspace per context
     const uint64_t cap_words = capacity_bytes / 4;
-    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s); launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, ctx->d_flat, s); }
-    { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, (uint64_t)n * g.nb, ctx->d_table, ctx->d_bits, s); }
-    bool fused;
-    { KernelTimer t(ctx, FLIC_K_SLOTS, s);
-      fused = launch_slots(g, ctx->d_bits, ctx->d_dirE, ctx->d_slot_status, ++ctx->slot_epoch, cap_words, ctx->d_err,
-                           (uint32_t *)d_streams, (unsigned long long *)d_offsets, s); }
-    if (!fused) {  // headers and directories depend on the slots only: before k_pack, off its tail
-        KernelTimer t(ctx, FLIC_K_FINALIZE, s);
-        launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s);
+    if (!staged) {
+        // fused single pass (k_encode) + headers/directories (k_finalize)
+        if (++ctx->fused_epoch >= (1u << 22)) {  // the 22-bit epoch wrapped: start over on a clean status array
+            CU(cudaMemsetAsync(ctx->d_status, 0, ctx->ws_blocks * sizeof(unsigned long long), s));
+            ctx->fused_epoch = 1;
+        }
+        unsigned grid;
+        { KernelTimer t(ctx, FLIC_K_ENCODE, s);
+          grid = launch_encode_fused(d_pixels, g, (uint32_t *)d_streams, cap_words, ctx->d_dirE, ctx->d_status, ctx->d_ticket,
+                                     ctx->ticket_base, ctx->fused_epoch, ctx->d_err, s); }
+        ctx->ticket_base += (uint64_t)n * g.nb + grid;  // every CTA's last claim fails
+        { KernelTimer t(ctx, FLIC_K_FINALIZE, s);
+          launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s); }
+        ctx->launches += 2;
+    } else {
+        { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s); launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, ctx->d_flat, s); }
+        { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, (uint64_t)n * g.nb, ctx->d_table, ctx->d_bits, s); }
+        bool fused;
+        { KernelTimer t(ctx, FLIC_K_SLOTS, s);
+          fused = launch_slots(g, ctx->d_bits, ctx->d_dirE, ctx->d_slot_status, ++ctx->slot_epoch, cap_words, ctx->d_err,
+                               (uint32_t *)d_streams, (unsigned long long *)d_offsets, ctx->slots_max_grid, s); }
+        if (!fused) {  // headers and directories depend on the slots only: before k_pack, off its tail
+            KernelTimer t(ctx, FLIC_K_FINALIZE, s);
+            launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s);
+        }
+        { KernelTimer t(ctx, FLIC_K_PACK, s);
+          launch_pack(ctx->d_resid, g, ctx->d_table, ctx->d_flat, (uint32_t *)d_streams, cap_words, ctx->d_dirE, ctx->d_err, s); }
+        ctx->launches += fused ? 4 : 5;
     }
-    { KernelTimer t(ctx, FLIC_K_PACK, s);
-      launch_pack(ctx->d_resid, g, ctx->d_table, ctx->d_flat, (uint32_t *)d_streams, cap_words, ctx->d_dirE, ctx->d_err, s); }
-    ctx->launches += fused ? 4 : 5;
+    CU(cudaEventRecord(ctx->ev_ws, s));
+    ctx->ws_stream = s; ctx->ws_used = true;
     CU(cudaGetLastError());
     return FLIC_OK;
 }
 
-// TMA descriptor of a tightly packed RGBA pixel batch for k_decode's store path: 3-D {row bytes, rows,
-// images}, 64 B x 32 rows boxes, 64 B swizzle.  Returns false when the layout does not qualify (then the
-// kernel stores directly) or the driver entry point is missing.
-static bool make_pixel_map(const Geo &g, uint8_t *d_pixels, CUtensorMap *tm) {
+// TMA descriptor of a tightly packed pixel batch for the decoders' store path: 3-D {row bytes, rows, images},
+// box_bytes x 32 rows boxes.  Returns false when the layout does not qualify (then the kernel stores directly)
+// or the driver entry point is missing.
+static bool make_pixel_map(const Geo &g, uint8_t *d_pixels, uint32_t box_bytes, CUtensorMapSwizzle swz, CUtensorMap *tm) {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -256,12 +363,12 @@ static bool make_pixel_map(const Geo &g, uint8_t *d_pixels, CUtensorMap *tm) {
         return (encode_fn)fn;
     }();
     static const bool off = getenv("FLIC_NO_TMA") != nullptr;
-    if (off || !encode || g.c != 4 || !g.aligned16) return false;
+    if (off || !encode || !g.aligned16) return false;
     const cuuint64_t dims[3] = {g.pitch, g.h, g.n};
     const cuuint64_t strides[2] = {g.pitch, g.img_stride};
-    const cuuint32_t box[3] = {64, (cuuint32_t)kBH, 1}, estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {box_bytes, (cuuint32_t)kBH, 1}, estr[3] = {1, 1, 1};
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pixels, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 extern "C" int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams, const uint64_t *d_offsets, uint32_t n,
@@ -272,11 +379,16 @@ extern "C" int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams,
     int rc = make_geo(d_pixels, n, w, h, c, flags, &g);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
-    { KernelTimer t(ctx, FLIC_K_DECODE, (cudaStream_t)stream);
-      alignas(64) CUtensorMap tm;
-      const bool tma = make_pixel_map(g, d_pixels, &tm);
-      launch_decode((const uint32_t *)d_streams, (const unsigned long long *)d_offsets, g, d_pixels, ctx->d_err,
-                    tma ? &tm : nullptr, (cudaStream_t)stream); }
+    if (flags & FLIC_FLAG_ONE_STREAM) {
+        KernelTimer t(ctx, FLIC_K_DECODE_ONE, (cudaStream_t)stream);
+        launch_decode_one((const uint32_t *)d_streams, (const unsigned long long *)d_offsets, g, d_pixels, ctx->d_err + 1, (cudaStream_t)stream);
+    } else {
+        KernelTimer t(ctx, FLIC_K_DECODE, (cudaStream_t)stream);
+        alignas(64) CUtensorMap tm;
+        const bool tma = g.c == 4 && make_pixel_map(g, d_pixels, 64, CU_TENSOR_MAP_SWIZZLE_64B, &tm);
+        launch_decode((const uint32_t *)d_streams, (const unsigned long long *)d_offsets, g, d_pixels, ctx->d_err + 1,
+                      tma ? &tm : nullptr, (cudaStream_t)stream);
+    }
     ctx->launches += 1;
     CU(cudaGetLastError());
     return FLIC_OK;
@@ -291,60 +403,108 @@ extern "C" int flic_set_kernel_timing(flic_ctx *ctx, int enable) {
 extern "C" int flic_get_kernel_times(flic_ctx *ctx, double ms[FLIC_K_COUNT], uint64_t counts[FLIC_K_COUNT]) {
     if (!ctx || !ms || !counts) return FLIC_E_ARG;
     for (int i = 0; i < FLIC_K_COUNT; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    int rc = FLIC_OK;
+    std::lock_guard<std::mutex> lk(ctx->span_mu);
     for (auto &sp : ctx->spans) {
-        CU(cudaEventSynchronize(sp.b));
         float t = 0.f;
-        CU(cudaEventElapsedTime(&t, sp.a, sp.b));
-        ms[sp.kernel] += t;
-        counts[sp.kernel] += 1;
+        cudaError_t e = cudaEventSynchronize(sp.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, sp.a, sp.b);
+        if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "kernel timing events"); }
+        else { ms[sp.kernel] += t; counts[sp.kernel] += 1; }
         ctx->free_spans.push_back(sp);
     }
     ctx->spans.clear();
-    return FLIC_OK;
+    return rc;
+}
+
+static int report_device_errors(flic_ctx *ctx, uint32_t e) {
+    if (!e) return FLIC_OK;
+    snprintf(ctx->msg, sizeof ctx->msg, "device error bits 0x%x%s%s%s%s", e, (e & kErrCapacity) ? " capacity" : "",
+             (e & kErrSlot) ? " slot-overrun" : "", (e & kErrFormat) ? " format" : "", (e & kErrRange) ? " payload-exceeds-u32-words" : "");
+    if (e & kErrFormat) return FLIC_E_FORMAT;
+    if (e & kErrCapacity) return FLIC_E_CAPACITY;
+    if (e & kErrRange) return FLIC_E_UNSUPPORTED;
+    return FLIC_E_INTERNAL;
+}
+
+// One direction's error word (0 encode, 1 decode), read and cleared on `s` through that direction's own pinned word.
+static int check_word(flic_ctx *ctx, int word, cudaStream_t s) {
+    CU(cudaMemcpyAsync(ctx->h_err + word, ctx->d_err + word, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemsetAsync(ctx->d_err + word, 0, sizeof(uint32_t), s));
+    CU(cudaStreamSynchronize(s));
+    return report_device_errors(ctx, ctx->h_err[word]);
 }
 
 extern "C" int flic_check(flic_ctx *ctx, void *stream) {
     if (!ctx) return FLIC_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaSetDevice(ctx->device));
-    CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(uint32_t), s));
+    CU(cudaMemcpyAsync(ctx->h_err + 2, ctx->d_err, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemsetAsync(ctx->d_err, 0, 2 * sizeof(uint32_t), s));
     CU(cudaStreamSynchronize(s));
-    uint32_t e = *ctx->h_err;
-    if (!e) return FLIC_OK;
-    snprintf(ctx->msg, sizeof ctx->msg, "device error bits 0x%x%s%s%s", e, (e & kErrCapacity) ? " capacity" : "",
-             (e & kErrSlot) ? " slot-overrun" : "", (e & kErrFormat) ? " format" : "");
-    if (e & kErrFormat) return FLIC_E_FORMAT;
-    if (e & kErrCapacity) return FLIC_E_CAPACITY;
-    return FLIC_E_INTERNAL;
+    return report_device_errors(ctx, ctx->h_err[2] | ctx->h_err[3]);
 }
 
 // ------------------------------------------------------------ host-buffer API
-static int ensure_staging(flic_ctx *ctx, uint64_t pix, uint64_t str, uint64_t noff) {
-    if (pix > ctx->pix_cap) {
-        for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_pix[i]); ctx->d_pix[i] = nullptr; }
-        ctx->pix_cap = 0;
-        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&ctx->d_pix[i], pix));
-        ctx->pix_cap = pix;
+extern "C" int flic_host_register(void *p, uint64_t bytes) {
+    if (!p || !bytes) return FLIC_E_ARG;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return FLIC_OK; }
+    return e == cudaSuccess ? FLIC_OK : FLIC_E_CUDA;
+}
+extern "C" int flic_host_unregister(void *p) {
+    if (!p) return FLIC_E_ARG;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) cudaGetLastError();
+    return e == cudaSuccess ? FLIC_OK : FLIC_E_CUDA;
+}
+
+namespace {
+// Pins a caller buffer for the duration of one host-API call when it is pageable: cudaMemcpyAsync on pageable
+// memory is staged through the driver's bounce buffer and serialises with the host, which turns the three-stream
+// pipeline into a sequence.  Buffers that are already pinned (cudaHostAlloc / flic_host_register — what a caller
+// on the fast path should do once, up front) are left alone; a failed registration just means the slow copies.
+struct AutoPin {
+    void *base = nullptr;
+    AutoPin(const void *p, uint64_t bytes) {
+        static const bool off = getenv("FLIC_NO_AUTOPIN") != nullptr;
+        if (off || !p || bytes < (1u << 20)) return;  // small buffers: registration costs more than it saves
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return; }
+        if (a.type != cudaMemoryTypeUnregistered) return;
+        const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)4095, hi = ((uintptr_t)p + bytes + 4095) & ~(uintptr_t)4095;
+        if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterPortable) == cudaSuccess) base = (void *)lo;
+        else cudaGetLastError();
     }
-    if (str > ctx->str_cap) {
-        for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_str[i]); ctx->d_str[i] = nullptr; }
-        ctx->str_cap = 0;
-        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&ctx->d_str[i], str + 16));
-        ctx->str_cap = str;
+    ~AutoPin() { if (base) cudaHostUnregister(base); }
+};
+}  // namespace
+
+static int ensure_staging(flic_ctx *ctx, Pipe &p, uint64_t pix, uint64_t str, uint64_t noff) {
+    if (pix > p.pix_cap) {
+        for (int i = 0; i < 2; ++i) { cudaFree(p.d_pix[i]); p.d_pix[i] = nullptr; }
+        p.pix_cap = 0;
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&p.d_pix[i], pix));
+        p.pix_cap = pix;
     }
-    if (noff > ctx->off_cap) {
+    if (str > p.str_cap) {
+        for (int i = 0; i < 2; ++i) { cudaFree(p.d_str[i]); p.d_str[i] = nullptr; }
+        p.str_cap = 0;
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&p.d_str[i], str + 16));
+        p.str_cap = str;
+    }
+    if (noff > p.off_cap) {
         for (int i = 0; i < 2; ++i) {
-            cudaFree(ctx->d_off[i]); ctx->d_off[i] = nullptr;
-            if (ctx->h_off[i]) cudaFreeHost(ctx->h_off[i]);
-            ctx->h_off[i] = nullptr;
+            cudaFree(p.d_off[i]); p.d_off[i] = nullptr;
+            if (p.h_off[i]) cudaFreeHost(p.h_off[i]);
+            p.h_off[i] = nullptr;
         }
-        ctx->off_cap = 0;
+        p.off_cap = 0;
         for (int i = 0; i < 2; ++i) {
-            CU(cudaMalloc(&ctx->d_off[i], noff * sizeof(unsigned long long)));
-            CU(cudaMallocHost(&ctx->h_off[i], noff * sizeof(unsigned long long)));
+            CU(cudaMalloc(&p.d_off[i], noff * sizeof(unsigned long long)));
+            CU(cudaMallocHost(&p.h_off[i], noff * sizeof(unsigned long long)));
         }
-        ctx->off_cap = noff;
+        p.off_cap = noff;
     }
     return FLIC_OK;
 }
@@ -362,21 +522,19 @@ static uint32_t chunk_images(uint32_t n, uint64_t image_bytes) {
     return (uint32_t)(m > n ? n : m);
 }
 
-static int drain(flic_ctx *ctx) {  // after a failure: leave no work in flight on the staging buffers
-    cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_out);
-    return 0;
+static void drain(Pipe &p) {  // after a failure: leave no work in flight on the staging or the caller's buffers
+    cudaStreamSynchronize(p.s_in); cudaStreamSynchronize(p.s_k); cudaStreamSynchronize(p.s_out);
 }
 
-extern "C" int flic_encode_batch(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n, uint32_t w, uint32_t h, uint32_t c,
-                                 uint32_t flags, uint8_t *h_streams, uint64_t capacity_bytes, uint64_t *h_offsets) {
-    if (!ctx || !h_pixels || !h_streams || !h_offsets) return FLIC_E_ARG;
-    if (n == 0 || w == 0 || h == 0 || c < 1 || c > 4) return FLIC_E_ARG;
-    if ((flags & 0x0Fu) != FLIC_PRED_LEFT || (flags & ~0x1Fu)) return FLIC_E_ARG;
+static int encode_batch_impl(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n, uint32_t w, uint32_t h, uint32_t c,
+                             uint32_t flags, uint8_t *h_streams, uint64_t capacity_bytes, uint64_t *h_offsets) {
+    Pipe &P = ctx->enc;
     const uint64_t img_bytes = (uint64_t)w * h * c, img_worst = flic_max_stream_bytes(w, h, c);
     const uint32_t m = chunk_images(n, img_bytes);
     CU(cudaSetDevice(ctx->device));
-    int rc = ensure_staging(ctx, m * img_bytes, m * img_worst, (uint64_t)m + 1);
+    int rc = ensure_staging(ctx, P, m * img_bytes, m * img_worst, (uint64_t)m + 1);
     if (rc) return rc;
+    AutoPin pin_in(h_pixels, (uint64_t)n * img_bytes), pin_out(h_streams, capacity_bytes);
     const uint32_t chunks = (n + m - 1) / m;
     uint64_t out_pos = 0;
     h_offsets[0] = 0;
@@ -384,10 +542,9 @@ extern "C" int flic_encode_batch(flic_ctx *ctx, const uint8_t *h_pixels, uint32_
     auto issue_in = [&](uint32_t k) -> int {
         const int b = k & 1;
         const uint32_t first = k * m, cnt = (first + m <= n) ? m : n - first;
-        if (k >= 2) CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_k[b], 0));  // kernels of chunk k-2 have consumed d_pix[b]
-        CU(cudaMemcpyAsync(ctx->d_pix[b], h_pixels + (uint64_t)first * img_bytes, cnt * img_bytes, cudaMemcpyHostToDevice,
-                           ctx->s_in));
-        CU(cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+        if (k >= 2) CU(cudaStreamWaitEvent(P.s_in, P.ev_k[b], 0));  // kernels of chunk k-2 have consumed d_pix[b]
+        CU(cudaMemcpyAsync(P.d_pix[b], h_pixels + (uint64_t)first * img_bytes, cnt * img_bytes, cudaMemcpyHostToDevice, P.s_in));
+        CU(cudaEventRecord(P.ev_in[b], P.s_in));
         return FLIC_OK;
     };
     rc = issue_in(0);
@@ -395,29 +552,45 @@ extern "C" int flic_encode_batch(flic_ctx *ctx, const uint8_t *h_pixels, uint32_
         const int b = k & 1;
         const uint32_t first = k * m, cnt = (first + m <= n) ? m : n - first;
         rc = [&]() -> int {
-            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
-            if (k >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));  // D2H of chunk k-2 has drained d_str[b]
-            int r = flic_encode_batch_device(ctx, ctx->d_pix[b], cnt, w, h, c, flags, ctx->d_str[b], cnt * img_worst,
-                                             (uint64_t *)ctx->d_off[b], ctx->stream);
+            CU(cudaStreamWaitEvent(P.s_k, P.ev_in[b], 0));
+            if (k >= 2) CU(cudaStreamWaitEvent(P.s_k, P.ev_out[b], 0));  // D2H of chunk k-2 has drained d_str[b]
+            int r = flic_encode_batch_device(ctx, P.d_pix[b], cnt, w, h, c, flags, P.d_str[b], cnt * img_worst,
+                                             (uint64_t *)P.d_off[b], P.s_k);
             if (r) return r;
-            CU(cudaMemcpyAsync(ctx->h_off[b], ctx->d_off[b], ((uint64_t)cnt + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+            CU(cudaMemcpyAsync(P.h_off[b], P.d_off[b], ((uint64_t)cnt + 1) * 8, cudaMemcpyDeviceToHost, P.s_k));
+            CU(cudaEventRecord(P.ev_k[b], P.s_k));
             if (k + 1 < chunks) { r = issue_in(k + 1); if (r) return r; }
-            CU(cudaEventSynchronize(ctx->ev_k[b]));
-            const uint64_t total = ctx->h_off[b][cnt];
+            CU(cudaEventSynchronize(P.ev_k[b]));
+            const uint64_t total = P.h_off[b][cnt];
             if (total > cnt * img_worst) return FLIC_E_INTERNAL;  // kernels flagged a capacity overrun
             if (out_pos + total > capacity_bytes) return FLIC_E_CAPACITY;
-            for (uint32_t i = 1; i <= cnt; ++i) h_offsets[first + i] = out_pos + ctx->h_off[b][i];
-            CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[b], 0));
-            CU(cudaMemcpyAsync(h_streams + out_pos, ctx->d_str[b], total, cudaMemcpyDeviceToHost, ctx->s_out));
-            CU(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
+            for (uint32_t i = 1; i <= cnt; ++i) h_offsets[first + i] = out_pos + P.h_off[b][i];
+            CU(cudaStreamWaitEvent(P.s_out, P.ev_k[b], 0));
+            CU(cudaMemcpyAsync(h_streams + out_pos, P.d_str[b], total, cudaMemcpyDeviceToHost, P.s_out));
+            CU(cudaEventRecord(P.ev_out[b], P.s_out));
             out_pos += total;
             return FLIC_OK;
         }();
     }
-    if (rc) { drain(ctx); flic_check(ctx, ctx->stream); return rc; }
-    CU(cudaStreamSynchronize(ctx->s_out));
-    return flic_check(ctx, ctx->stream);
+    drain(P);  // success or not: nothing may touch the caller's buffers after the call returns
+    const int chk = check_word(ctx, 0, P.s_k);
+    return rc ? rc : chk;
+}
+
+static int encode_args_ok(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n, uint32_t w, uint32_t h, uint32_t c,
+                          uint32_t flags, uint8_t *h_streams, uint64_t *h_offsets) {
+    if (!ctx || !h_pixels || !h_streams || !h_offsets) return FLIC_E_ARG;
+    if (n == 0 || w == 0 || h == 0 || c < 1 || c > 4 || !flags_ok(flags)) return FLIC_E_ARG;
+    if (cdiv(w, kBW) * cdiv(h, kBH) > 0xFFFFFFFFull) return FLIC_E_ARG;
+    return FLIC_OK;
+}
+
+extern "C" int flic_encode_batch(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n, uint32_t w, uint32_t h, uint32_t c,
+                                 uint32_t flags, uint8_t *h_streams, uint64_t capacity_bytes, uint64_t *h_offsets) {
+    int rc = encode_args_ok(ctx, h_pixels, n, w, h, c, flags, h_streams, h_offsets);
+    if (rc) return rc;
+    if (ctx->enc.busy) return FLIC_E_BUSY;
+    return encode_batch_impl(ctx, h_pixels, n, w, h, c, flags, h_streams, capacity_bytes, h_offsets);
 }
 
 extern "C" int flic_peek(const uint8_t *s, uint64_t size, flic_image_info *info) {
@@ -434,68 +607,225 @@ extern "C" int flic_peek(const uint8_t *s, uint64_t size, flic_image_info *info)
     info->n_blocks = wd[5];
     info->payload_words = wd[6];
     if (info->width == 0 || info->height == 0 || info->channels < 1 || info->channels > 4) return FLIC_E_FORMAT;
-    if ((info->flags & 0x0Fu) != FLIC_PRED_LEFT || (info->flags & ~0x1Fu)) return FLIC_E_FORMAT;
+    if (!flags_ok(info->flags)) return FLIC_E_FORMAT;
     if (info->block_w == 0 || info->block_h == 0 || (info->block_h & 1)) return FLIC_E_FORMAT;
-    if ((uint64_t)cdiv(info->width, info->block_w) * cdiv(info->height, info->block_h) != info->n_blocks)
-        return FLIC_E_FORMAT;
+    if (cdiv(info->width, info->block_w) * cdiv(info->height, info->block_h) != info->n_blocks) return FLIC_E_FORMAT;
     if (4ull * (kHdrWords + (uint64_t)info->n_blocks + 1 + info->payload_words) > size) return FLIC_E_FORMAT;
     return FLIC_OK;
+}
+
+// Decodes the streams [lo, hi) of a batch, all of one geometry `g0`, through the decode pipe.
+static int decode_run(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h_offsets, uint32_t lo, uint32_t hi,
+                      const flic_image_info &g0, uint8_t *h_pixels) {
+    Pipe &P = ctx->dec;
+    const uint32_t n = hi - lo;
+    const uint64_t img_bytes = (uint64_t)g0.width * g0.height * g0.channels;
+    const uint32_t m = chunk_images(n, img_bytes);
+    const uint32_t chunks = (n + m - 1) / m;
+    uint64_t max_str = 0;
+    for (uint32_t k = 0; k < chunks; ++k) {
+        const uint32_t f0 = lo + k * m, f1 = (f0 + m <= hi) ? f0 + m : hi;
+        const uint64_t sz = h_offsets[f1] - h_offsets[f0];
+        if (sz > max_str) max_str = sz;
+    }
+    int rc = ensure_staging(ctx, P, m * img_bytes, max_str, (uint64_t)m + 1);
+    if (rc) return rc;
+    for (uint32_t k = 0; k < chunks && rc == FLIC_OK; ++k) {
+        const int b = k & 1;
+        const uint32_t f0 = lo + k * m, cnt = (f0 + m <= hi) ? m : hi - f0;
+        const uint64_t base = h_offsets[f0], sz = h_offsets[f0 + cnt] - base;
+        rc = [&]() -> int {
+            // the pinned offsets and d_str[b] of chunk k-2 must have been consumed by its kernel
+            if (k >= 2) CU(cudaEventSynchronize(P.ev_k[b]));
+            for (uint32_t i = 0; i <= cnt; ++i) P.h_off[b][i] = h_offsets[f0 + i] - base;
+            CU(cudaMemcpyAsync(P.d_str[b], h_streams + base, sz, cudaMemcpyHostToDevice, P.s_in));
+            CU(cudaMemcpyAsync(P.d_off[b], P.h_off[b], ((uint64_t)cnt + 1) * 8, cudaMemcpyHostToDevice, P.s_in));
+            CU(cudaEventRecord(P.ev_in[b], P.s_in));
+            CU(cudaStreamWaitEvent(P.s_k, P.ev_in[b], 0));
+            if (k >= 2) CU(cudaStreamWaitEvent(P.s_k, P.ev_out[b], 0));  // D2H of chunk k-2 has drained d_pix[b]
+            int r = flic_decode_batch_device(ctx, P.d_str[b], (const uint64_t *)P.d_off[b], cnt, g0.width, g0.height,
+                                             g0.channels, g0.flags, P.d_pix[b], P.s_k);
+            if (r) return r;
+            CU(cudaEventRecord(P.ev_k[b], P.s_k));
+            CU(cudaStreamWaitEvent(P.s_out, P.ev_k[b], 0));
+            CU(cudaMemcpyAsync(h_pixels + (uint64_t)(f0 - lo) * img_bytes, P.d_pix[b], cnt * img_bytes, cudaMemcpyDeviceToHost, P.s_out));
+            CU(cudaEventRecord(P.ev_out[b], P.s_out));
+            return FLIC_OK;
+        }();
+    }
+    drain(P);
+    return rc;
+}
+
+static bool same_geometry(const flic_image_info &a, const flic_image_info &b) {
+    return a.width == b.width && a.height == b.height && a.channels == b.channels &&
+           ((a.flags ^ b.flags) & ~FLIC_FLAG_EXACT) == 0;  // EXACT does not change how a stream decodes
+}
+
+static int decode_batch_impl(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h_offsets, uint32_t n,
+                             uint8_t *h_pixels, uint64_t pixels_capacity) {
+    // A batch may mix geometries: it is decoded as runs of consecutive streams of one geometry, one launch
+    // sequence per run, pixels tightly packed in stream order.
+    std::vector<flic_image_info> infos(n);
+    uint64_t need = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (h_offsets[i + 1] < h_offsets[i] || (h_offsets[i] & 3u)) return FLIC_E_FORMAT;
+        int rc = flic_peek(h_streams + h_offsets[i], h_offsets[i + 1] - h_offsets[i], &infos[i]);
+        if (rc) return rc;
+        if (infos[i].block_w != (uint32_t)kBW || infos[i].block_h != (uint32_t)kBH) return FLIC_E_UNSUPPORTED;
+        need += (uint64_t)infos[i].width * infos[i].height * infos[i].channels;
+    }
+    if (need > pixels_capacity) return FLIC_E_CAPACITY;
+    CU(cudaSetDevice(ctx->device));
+    AutoPin pin_in(h_streams + h_offsets[0], h_offsets[n] - h_offsets[0]), pin_out(h_pixels, need);
+    int rc = FLIC_OK;
+    uint64_t pix_pos = 0;
+    for (uint32_t lo = 0; lo < n && rc == FLIC_OK;) {
+        uint32_t hi = lo + 1;
+        while (hi < n && same_geometry(infos[hi], infos[lo])) ++hi;
+        rc = decode_run(ctx, h_streams, h_offsets, lo, hi, infos[lo], h_pixels + pix_pos);
+        pix_pos += (uint64_t)(hi - lo) * infos[lo].width * infos[lo].height * infos[lo].channels;
+        lo = hi;
+    }
+    const int chk = check_word(ctx, 1, ctx->dec.s_k);
+    return rc ? rc : chk;
 }
 
 extern "C" int flic_decode_batch(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h_offsets, uint32_t n,
                                  uint8_t *h_pixels, uint64_t pixels_capacity) {
     if (!ctx || !h_streams || !h_offsets || !h_pixels || n == 0) return FLIC_E_ARG;
-    flic_image_info first;
-    for (uint32_t i = 0; i < n; ++i) {
-        if (h_offsets[i + 1] < h_offsets[i] || (h_offsets[i] & 3u)) return FLIC_E_FORMAT;
-        flic_image_info info;
-        int rc = flic_peek(h_streams + h_offsets[i], h_offsets[i + 1] - h_offsets[i], &info);
-        if (rc) return rc;
-        if (info.block_w != (uint32_t)kBW || info.block_h != (uint32_t)kBH) return FLIC_E_UNSUPPORTED;
-        if (i == 0) first = info;
-        else if (info.width != first.width || info.height != first.height || info.channels != first.channels ||
-                 info.flags != first.flags)
-            return FLIC_E_UNSUPPORTED;  // one launch decodes one geometry; split mixed batches by geometry
-    }
-    const uint64_t img_bytes = (uint64_t)first.width * first.height * first.channels;
-    if ((uint64_t)n * img_bytes > pixels_capacity) return FLIC_E_CAPACITY;
-    const uint32_t m = chunk_images(n, img_bytes);
-    const uint32_t chunks = (n + m - 1) / m;
-    uint64_t max_str = 0;
-    for (uint32_t k = 0; k < chunks; ++k) {
-        const uint32_t f0 = k * m, f1 = (f0 + m <= n) ? f0 + m : n;
-        const uint64_t sz = h_offsets[f1] - h_offsets[f0];
-        if (sz > max_str) max_str = sz;
-    }
-    CU(cudaSetDevice(ctx->device));
-    int rc = ensure_staging(ctx, m * img_bytes, max_str, (uint64_t)m + 1);
+    if (ctx->dec.busy) return FLIC_E_BUSY;
+    return decode_batch_impl(ctx, h_streams, h_offsets, n, h_pixels, pixels_capacity);
+}
+
+// ---- submit / wait: the same pipelines on a worker thread, so that one call's D2H overlaps another's H2D ----
+extern "C" int flic_encode_submit(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n, uint32_t w, uint32_t h, uint32_t c,
+                                  uint32_t flags, uint8_t *h_streams, uint64_t capacity_bytes, uint64_t *h_offsets) {
+    int rc = encode_args_ok(ctx, h_pixels, n, w, h, c, flags, h_streams, h_offsets);
     if (rc) return rc;
-    for (uint32_t k = 0; k < chunks; ++k) {
-        const int b = k & 1;
-        const uint32_t f0 = k * m, cnt = (f0 + m <= n) ? m : n - f0;
-        const uint64_t base = h_offsets[f0], sz = h_offsets[f0 + cnt] - base;
-        // the pinned offsets and d_str[b] of chunk k-2 must have been consumed by its kernel
-        if (k >= 2) { CU(cudaEventSynchronize(ctx->ev_k[b])); }
-        for (uint32_t i = 0; i <= cnt; ++i) ctx->h_off[b][i] = h_offsets[f0 + i] - base;
-        CU(cudaMemcpyAsync(ctx->d_str[b], h_streams + base, sz, cudaMemcpyHostToDevice, ctx->s_in));
-        CU(cudaMemcpyAsync(ctx->d_off[b], ctx->h_off[b], ((uint64_t)cnt + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-        CU(cudaEventRecord(ctx->ev_in[b], ctx->s_in));
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
-        if (k >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));  // D2H of chunk k-2 has drained d_pix[b]
-        rc = flic_decode_batch_device(ctx, ctx->d_str[b], (const uint64_t *)ctx->d_off[b], cnt, first.width, first.height,
-                                      first.channels, first.flags, ctx->d_pix[b], ctx->stream);
-        if (rc) { drain(ctx); return rc; }
-        CU(cudaEventRecord(ctx->ev_k[b], ctx->stream));
-        CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[b], 0));
-        CU(cudaMemcpyAsync(h_pixels + (uint64_t)f0 * img_bytes, ctx->d_pix[b], cnt * img_bytes, cudaMemcpyDeviceToHost,
-                           ctx->s_out));
-        CU(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
-    }
-    CU(cudaStreamSynchronize(ctx->s_out));
-    return flic_check(ctx, ctx->stream);
+    Pipe &P = ctx->enc;
+    if (P.busy) return FLIC_E_BUSY;
+    P.busy = true;
+    P.worker = std::thread([=, &P] { P.result = encode_batch_impl(ctx, h_pixels, n, w, h, c, flags, h_streams, capacity_bytes, h_offsets); });
+    return FLIC_OK;
+}
+
+extern "C" int flic_decode_submit(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h_offsets, uint32_t n,
+                                  uint8_t *h_pixels, uint64_t pixels_capacity) {
+    if (!ctx || !h_streams || !h_offsets || !h_pixels || n == 0) return FLIC_E_ARG;
+    Pipe &P = ctx->dec;
+    if (P.busy) return FLIC_E_BUSY;
+    P.busy = true;
+    P.worker = std::thread([=, &P] { P.result = decode_batch_impl(ctx, h_streams, h_offsets, n, h_pixels, pixels_capacity); });
+    return FLIC_OK;
+}
+
+extern "C" int flic_wait(flic_ctx *ctx, int op) {
+    if (!ctx || (op != FLIC_OP_ENCODE && op != FLIC_OP_DECODE)) return FLIC_E_ARG;
+    Pipe &P = op == FLIC_OP_ENCODE ? ctx->enc : ctx->dec;
+    if (!P.busy) return FLIC_E_ARG;
+    P.worker.join();
+    P.busy = false;
+    return P.result;
 }
 
 // ------------------------------------------------------------------- splice
+extern "C" int flic_splice_plan(const uint32_t *part_blocks, const uint32_t *part_payload_words, uint32_t k,
+                                uint64_t *dir_byte_off, uint64_t *payload_byte_off, uint64_t *total_bytes) {
+    if (!part_blocks || !part_payload_words || !dir_byte_off || !payload_byte_off || !total_bytes || k == 0) return FLIC_E_ARG;
+    uint64_t nb = 0, pw = 0;
+    for (uint32_t i = 0; i < k; ++i) { nb += part_blocks[i]; pw += part_payload_words[i]; }
+    if (nb >= (1ull << 32) || pw >= (1ull << 32)) return FLIC_E_ARG;
+    uint64_t b = 0, p = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        dir_byte_off[i] = 4ull * (kHdrWords + b);
+        payload_byte_off[i] = 4ull * (kHdrWords + nb + 1 + p);
+        b += part_blocks[i]; p += part_payload_words[i];
+    }
+    *total_bytes = 4ull * (kHdrWords + nb + 1 + pw);
+    return FLIC_OK;
+}
+
+extern "C" int flic_splice_finish_device(flic_ctx *ctx, uint8_t *d_out, const uint32_t *part_blocks,
+                                         const uint32_t *part_payload_words, uint32_t k, uint32_t w, uint32_t h_total,
+                                         uint32_t c, uint32_t flags, void *stream) {
+    if (!ctx || !d_out || ((uintptr_t)d_out & 3u) || !part_blocks || !part_payload_words || k == 0 || k > FLIC_MAX_PARTS) return FLIC_E_ARG;
+    if (w == 0 || h_total == 0 || c < 1 || c > 4 || !flags_ok(flags)) return FLIC_E_ARG;
+    SpliceParts sp;
+    uint64_t nb = 0, pw = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        sp.first_block[i] = (uint32_t)nb; sp.base_words[i] = (uint32_t)pw;
+        nb += part_blocks[i]; pw += part_payload_words[i];
+    }
+    if (nb >= (1ull << 32) || pw >= (1ull << 32) || nb != cdiv(w, kBW) * cdiv(h_total, kBH)) return FLIC_E_ARG;
+    sp.first_block[k] = (uint32_t)nb; sp.base_words[k] = (uint32_t)pw;
+    sp.k = k;
+    CU(cudaSetDevice(ctx->device));
+    launch_splice_finish((uint32_t *)d_out, sp, w, h_total, c, flags, (cudaStream_t)stream);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return FLIC_OK;
+}
+
+extern "C" int flic_split_finish_device(flic_ctx *ctx, uint8_t *d_part, uint32_t w, uint32_t h_part, uint32_t c,
+                                        uint32_t flags, void *stream) {
+    if (!ctx || !d_part || ((uintptr_t)d_part & 3u) || w == 0 || h_part == 0 || c < 1 || c > 4 || !flags_ok(flags)) return FLIC_E_ARG;
+    const uint64_t nb = cdiv(w, kBW) * cdiv(h_part, kBH);
+    if (nb >= (1ull << 32)) return FLIC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    launch_split_finish((uint32_t *)d_part, (uint32_t)nb, w, h_part, c, flags, (cudaStream_t)stream);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return FLIC_OK;
+}
+
+extern "C" int flic_splice_block_rows_device(flic_ctx *ctx, const uint8_t *const *d_parts, const uint64_t *part_sizes,
+                                             uint32_t k, uint8_t *d_out, uint64_t out_capacity, uint64_t *out_size, void *stream) {
+    if (!ctx || !d_parts || !part_sizes || !d_out || !out_size || k == 0 || k > FLIC_MAX_PARTS) return FLIC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t hdr[FLIC_MAX_PARTS][FLIC_HEADER_BYTES];
+    for (uint32_t i = 0; i < k; ++i) {
+        if (!d_parts[i] || part_sizes[i] < FLIC_HEADER_BYTES || ((uintptr_t)d_parts[i] & 3u)) return FLIC_E_ARG;
+        CU(cudaMemcpyAsync(hdr[i], d_parts[i], FLIC_HEADER_BYTES, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    flic_image_info first, info;
+    uint32_t nbs[FLIC_MAX_PARTS], pws[FLIC_MAX_PARTS];
+    uint64_t height = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        // the header alone is on the host: check it against the part's size without touching the payload
+        memset(&info, 0, sizeof info);
+        uint8_t tmp[FLIC_HEADER_BYTES];
+        memcpy(tmp, hdr[i], sizeof tmp);
+        uint32_t wd[8];
+        memcpy(wd, tmp, sizeof wd);
+        if (4ull * (kHdrWords + (uint64_t)wd[5] + 1 + wd[6]) > part_sizes[i]) return FLIC_E_FORMAT;
+        int rc = flic_peek(tmp, part_sizes[i], &info);
+        if (rc) return rc;
+        if (i == 0) first = info;
+        else if (info.width != first.width || info.channels != first.channels || info.flags != first.flags ||
+                 info.block_w != first.block_w || info.block_h != first.block_h)
+            return FLIC_E_ARG;
+        if (i + 1 < k && info.height % info.block_h) return FLIC_E_ARG;  // only the last part may be ragged
+        nbs[i] = info.n_blocks; pws[i] = info.payload_words; height += info.height;
+    }
+    if (height >= (1ull << 32)) return FLIC_E_ARG;
+    uint64_t doff[FLIC_MAX_PARTS], poff[FLIC_MAX_PARTS], total = 0;
+    int rc = flic_splice_plan(nbs, pws, k, doff, poff, &total);
+    if (rc) return rc;
+    if (total > out_capacity) return FLIC_E_CAPACITY;
+    for (uint32_t i = 0; i < k; ++i) {
+        const uint8_t *pdir = d_parts[i] + 4 * kHdrWords;
+        CU(cudaMemcpyAsync(d_out + doff[i], pdir, 4ull * nbs[i], cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(d_out + poff[i], pdir + 4ull * (nbs[i] + 1), 4ull * pws[i], cudaMemcpyDeviceToDevice, s));
+    }
+    rc = flic_splice_finish_device(ctx, d_out, nbs, pws, k, first.width, (uint32_t)height, first.channels, first.flags, stream);
+    if (rc) return rc;
+    *out_size = total;
+    return FLIC_OK;
+}
+
 extern "C" int flic_splice_block_rows(const uint8_t *const *parts, const uint64_t *part_sizes, uint32_t k, uint8_t *out,
                                       uint64_t out_capacity, uint64_t *out_size) {
     if (!parts || !part_sizes || !out || !out_size || k == 0) return FLIC_E_ARG;

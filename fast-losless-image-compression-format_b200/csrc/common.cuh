@@ -19,6 +19,7 @@ constexpr int kLutSize = 1 << kL;
 constexpr int kHdrWords = 8;                 // 32-byte stream header
 constexpr int kFlatWord = 32 + kBH / 2;     // block header word holding the flat-channel mask; the values follow
 constexpr int kBlkHdrWords = kFlatWord + 2;  // 256 length nibbles + 32 u16 row word counts + flat mask + flat values
+constexpr int kBlkHdrWords1 = 32 + 2;        // FLIC_FLAG_ONE_STREAM: 256 length nibbles + flat mask + flat values, then one bit stream
 constexpr uint32_t kVersion = 3;
 constexpr int kRowWordsMax = (kBW * 4 * kL + 31) / 32;  // 160: worst-case words of one row sub-stream
 constexpr uint32_t kMagic = 0x30504C46u;
@@ -28,6 +29,10 @@ constexpr uint32_t kLenSole = 15;
 constexpr uint32_t kErrCapacity = 1u;
 constexpr uint32_t kErrFormat = 4u;
 constexpr uint32_t kErrSlot = 8u;  // a block outgrew the slot k_slots computed for it (internal error)
+constexpr uint32_t kErrRange = 16u;  // an image's payload does not fit the container's u32 word offsets
+
+__host__ __device__ __forceinline__ bool one_stream(uint32_t flags) { return (flags & FLIC_FLAG_ONE_STREAM) != 0; }
+__host__ __device__ __forceinline__ int blk_hdr_words(uint32_t flags) { return one_stream(flags) ? kBlkHdrWords1 : kBlkHdrWords; }
 
 struct Geo {
     uint32_t n, w, h, c, flags;
@@ -181,16 +186,34 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, uint2 *d_flat,
                        cudaStream_t s);
 void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s);
+void launch_tables_cta(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s);
+int slots_max_resident_ctas();  // how many k_slots CTAs this device keeps resident at once (occupancy API)
 bool launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_dirE, unsigned long long *d_status,
                   uint32_t epoch, uint64_t capacity_words, uint32_t *d_err, uint32_t *d_streams,
-                  unsigned long long *d_offsets, cudaStream_t s);
+                  unsigned long long *d_offsets, int max_grid, cudaStream_t s);
 void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, const uint2 *d_flat, uint32_t *d_streams,
                  uint64_t capacity_words, const unsigned long long *d_dirE, uint32_t *d_err, cudaStream_t s);
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,
                      uint64_t capacity_words, unsigned long long *d_offsets, uint32_t *d_err,
                      cudaStream_t s);
+// fused single-pass encoder; returns the grid size (every CTA draws one ticket beyond the last block)
+unsigned launch_encode_fused(const uint8_t *d_pixels, const Geo &g, uint32_t *d_streams, uint64_t capacity_words,
+                             unsigned long long *d_dirE, unsigned long long *d_status, unsigned long long *d_ticket,
+                             unsigned long long ticket_base, uint32_t epoch, uint32_t *d_err, cudaStream_t s);
 // tensor_map: a 128-byte CUtensorMap over the pixel buffer (api.cu: make_pixel_map), or nullptr
 void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offsets, const Geo &g,
                    uint8_t *d_pixels, uint32_t *d_err, const void *tensor_map, cudaStream_t s);
+void launch_decode_one(const uint32_t *d_streams, const unsigned long long *d_offsets, const Geo &g,
+                       uint8_t *d_pixels, uint32_t *d_err, cudaStream_t s);
+
+// block-row splice on the device (splice.cu)
+struct SpliceParts {
+    uint32_t k;
+    uint32_t first_block[FLIC_MAX_PARTS + 1];  // first block of each part in the spliced directory (+ total)
+    uint32_t base_words[FLIC_MAX_PARTS + 1];   // payload words before each part (+ total)
+};
+void launch_splice_finish(uint32_t *d_out, const SpliceParts &sp, uint32_t w, uint32_t h, uint32_t c, uint32_t flags,
+                          cudaStream_t s);
+void launch_split_finish(uint32_t *d_part, uint32_t nb, uint32_t w, uint32_t h, uint32_t c, uint32_t flags, cudaStream_t s);
 
 }  // namespace flic

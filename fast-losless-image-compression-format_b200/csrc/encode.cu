@@ -430,8 +430,8 @@ void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, 
 // Headers, rebased u32 directories and the n+1 stream offsets: all of it follows from dirE, so it needs
 // only k_slots' result (not k_pack's).  `first`/`stride` spread the items over whoever calls this.
 __device__ __forceinline__ void finalize_items(const Geo &g, const unsigned long long *dirE, uint32_t *streams,
-                                               uint64_t capacity_words, unsigned long long *offsets, uint64_t first_item,
-                                               uint64_t stride) {
+                                               uint64_t capacity_words, unsigned long long *offsets, uint32_t *err,
+                                               uint64_t first_item, uint64_t stride) {
     const uint64_t per = kHdrWords + (uint64_t)g.nb + 1;  // header + directory words per image
     const uint64_t items = (uint64_t)g.n * per;
     for (uint64_t i = first_item; i < items + g.n + 1; i += stride) {
@@ -455,7 +455,12 @@ __device__ __forceinline__ void finalize_items(const Geo &g, const unsigned long
                 case 3: v = g.h; break;
                 case 4: v = (uint32_t)kBW | ((uint32_t)kBH << 16); break;
                 case 5: v = g.nb; break;
-                case 6: v = (uint32_t)(dirE[(img + 1) * g.nb] - first); break;
+                case 6: {  // payload words: the container's offsets are u32
+                    const unsigned long long pw = dirE[(img + 1) * g.nb] - first;
+                    if (pw > 0xFFFFFFFFull) atomicOr(err, kErrRange);
+                    v = (uint32_t)pw;
+                    break;
+                }
                 default: v = (uint32_t)kL; break;
             }
         }
@@ -465,8 +470,8 @@ __device__ __forceinline__ void finalize_items(const Geo &g, const unsigned long
 
 __global__ void __launch_bounds__(256) k_finalize(Geo g, const unsigned long long *__restrict__ dirE,
                                                   uint32_t *__restrict__ streams, uint64_t capacity_words,
-                                                  unsigned long long *__restrict__ offsets) {
-    finalize_items(g, dirE, streams, capacity_words, offsets, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                                                  unsigned long long *__restrict__ offsets, uint32_t *err) {
+    finalize_items(g, dirE, streams, capacity_words, offsets, err, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x,
                    (uint64_t)gridDim.x * blockDim.x);
 }
 
@@ -541,19 +546,31 @@ __global__ void __launch_bounds__(kSlotThreads) k_slots(Geo g, const uint32_t *_
     }
     if (gridDim.x == 1 && streams) {  // small job, one CTA: write the headers and directories here, save a launch
         __syncthreads();
-        finalize_items(g, dirE, streams, capacity_words, offsets, tid, kSlotThreads);
+        finalize_items(g, dirE, streams, capacity_words, offsets, err, tid, kSlotThreads);
     }
 }
 
+// CTAs of k_slots spin on their predecessors' published sums, so every CTA of the grid must be resident at once:
+// the bound comes from the occupancy API, not from an assumption about the device.
+int slots_max_resident_ctas() {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_slots, kSlotThreads, 0) != cudaSuccess)
+        return 0;
+    const int n = sms * per_sm;
+    return n > 128 ? 128 : n;  // the status array holds 128 run sums
+}
+
 // status: >= 128 u64, zeroed once at allocation; epoch: a value never used before on this status array (>= 1)
+// max_grid: slots_max_resident_ctas() of the device (1..128).
 // Returns true when the (single) CTA also wrote headers and directories, i.e. k_finalize is not needed.
 bool launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_dirE, unsigned long long *d_status,
                   uint32_t epoch, uint64_t capacity_words, uint32_t *d_err, uint32_t *d_streams,
-                  unsigned long long *d_offsets, cudaStream_t s) {
+                  unsigned long long *d_offsets, int max_grid, cudaStream_t s) {
     const uint64_t total = (uint64_t)g.n * g.nb;
-    uint64_t per = (total + 127) / 128;
+    uint64_t per = (total + max_grid - 1) / max_grid;
     per = ((per < 2048 ? 2048 : per) + kSlotThreads - 1) / kSlotThreads * kSlotThreads;
-    const unsigned grid = (unsigned)((total + per - 1) / per);  // <= 128: all CTAs are resident, the spin cannot deadlock
+    const unsigned grid = (unsigned)((total + per - 1) / per);  // <= max_grid: all CTAs are resident, the spin cannot deadlock
     k_slots<<<grid, kSlotThreads, 0, s>>>(g, d_bits, d_dirE, (uint32_t)per, epoch, d_status, capacity_words, d_err, d_streams,
                                           d_offsets);
     return grid == 1;
@@ -774,11 +791,550 @@ void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table,
 }
 
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,
-                     uint64_t capacity_words, unsigned long long *d_offsets, uint32_t *, cudaStream_t s) {
+                     uint64_t capacity_words, unsigned long long *d_offsets, uint32_t *d_err, cudaStream_t s) {
     uint64_t items = (uint64_t)g.n * (kHdrWords + (uint64_t)g.nb + 1) + g.n + 1;
     uint64_t want = (items + 255) / 256;
     unsigned grid = (unsigned)(want < 148ull * 8 ? want : 148ull * 8);
-    k_finalize<<<grid, 256, 0, s>>>(g, d_dirE, d_streams, capacity_words, d_offsets);
+    k_finalize<<<grid, 256, 0, s>>>(g, d_dirE, d_streams, capacity_words, d_offsets, d_err);
+}
+
+
+// =============================================================================== k_encode (fused)
+// Round 2: the whole encode path in ONE pass over the pixels.  A persistent CTA claims blocks in order
+// (a ticket counter), and for each block: loads its rows, computes residuals and parks them in a shared
+// tile (16 KB that the staged path wrote to and re-read from HBM), histograms them, builds the code table
+// with the whole CTA (rank sort, one-thread two-queue merge with both queue heads in registers, depths by
+// pointer jumping, depth census, Kraft repair, canonical codes by MATCH.ANY), packs the rows over the same
+// tile, obtains its output position with a decoupled look-back over the predecessors' sizes, and copies
+// the block out.  DRAM traffic: N read + r.N written (+ 8 B of status and 8 B of directory per block).
+//
+// The look-back serves all three layouts: with slots (plain FLP0 v3) a block publishes its size as soon
+// as its table exists, before packing; with FLIC_FLAG_EXACT the size is only known after packing (the
+// pessimistic case: "block sizes are not known before packing"); with FLIC_FLAG_ONE_STREAM the size is
+// ceil(code bits / 32) and the rows are concatenated bit-exactly on the way out.
+constexpr int kFusedCtas = 6;  // resident CTAs per SM the register budget is set for
+constexpr uint32_t kInf = 0x7FFFFFFFu;
+
+struct TabScratch {           // aliases the sub-histograms (dead once every thread holds its symbol's count)
+    uint32_t key[256 + 4];    // compacted (count << 8 | symbol), padded with ~0 to a multiple of four
+    uint32_t W[256];          // leaf weights, ascending
+    uint32_t IW[256];         // internal-node weights in creation order (ascending too)
+    uint16_t P[256], D[256];  // parent / distance-to-P of internal nodes (pointer jumping -> depth)
+    uint32_t cntd[256];       // internal nodes per depth
+    uint8_t ord[256];         // symbol of each sorted rank
+    uint8_t lenS[256];        // code length per symbol
+    uint32_t num[16];         // leaves per code length
+    uint32_t next[16];        // first canonical code per length
+    uint32_t wcnt[kEncWarps][16];  // per warp: symbols of each length
+    uint32_t wused[kEncWarps];     // per warp: used symbols
+    uint32_t bits;
+};
+static_assert(sizeof(TabScratch) <= kEncWarps * 256 * 4, "table scratch must fit in the sub-histograms");
+
+// FLP0 §3.3 step 2 for one thread: leaves W[0..n) ascending -> parents P[q] of the internal nodes q < n-2
+// (node k is created in step k; n-2 is the root).  Both queues' first two entries live in registers and the
+// loads that replace them are issued two picks ahead, so the loop-carried chain is compare + select + add.
+// A leaf wins a tie against an internal node (oracle: flp0_build_lengths).
+__device__ __forceinline__ void two_queue_merge(const uint32_t *W, uint32_t *IW, uint16_t *P, int n) {
+    int leaf = 0, root = 0;
+    uint32_t lw = W[0], lw1 = W[1], lw2 = n > 2 ? W[2] : kInf;
+    uint32_t iw = kInf, iw1 = kInf;
+    for (int k = 0; k < n - 1; ++k) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (lw <= iw) {
+                sum += lw; ++leaf;
+                lw = lw1; lw1 = lw2; lw2 = leaf + 2 < n ? W[leaf + 2] : kInf;
+            } else {
+                sum += iw; P[root] = (uint16_t)k; ++root;
+                iw = iw1; iw1 = root + 1 < k ? IW[root + 1] : kInf;
+            }
+        }
+        IW[k] = sum;
+        if (root == k) iw = sum; else if (root + 1 == k) iw1 = sum;  // node k joins the internal queue
+    }
+}
+
+// Code table of one block, built by the whole CTA (256 threads; thread = symbol).  cnt: this symbol's
+// count.  Writes tab[s] = code | len << 24 (0: no bits) and nib[s] = length nibble (15: sole symbol);
+// returns sum of count x length.  Same rules as oracle/flp0_oracle.c flp0_build_lengths/flp0_assign_codes.
+__device__ uint32_t cta_table(uint32_t cnt, TabScratch &t, uint32_t *tab, uint8_t *nib, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t usedm = __ballot_sync(0xFFFFFFFFu, cnt != 0);
+    if (lane == 0) t.wused[warp] = __popc(usedm);
+    t.lenS[tid] = 0;
+    t.cntd[tid] = 0;
+    if (tid < 16) t.num[tid] = 0;
+    if (tid < kEncWarps * 16) (&t.wcnt[0][0])[tid] = 0;
+    if (tid == 0) t.bits = 0;
+    __syncthreads();
+    int before = 0, n = 0;
+#pragma unroll
+    for (int w = 0; w < kEncWarps; ++w) { const int u = (int)t.wused[w]; before += w < warp ? u : 0; n += u; }
+    if (n <= 1) {  // nothing to code: no symbols at all (every channel flat), or one symbol with a zero-length code
+        tab[tid] = 0;
+        nib[tid] = cnt ? (uint8_t)kLenSole : (uint8_t)0;
+        __syncthreads();
+        return 0;
+    }
+    if (cnt) t.key[before + __popc(usedm & lt)] = (cnt << 8) | (uint32_t)tid;
+    if (tid >= n && tid < ((n + 3) & ~3)) t.key[tid] = 0xFFFFFFFFu;
+    __syncthreads();
+    // (1) sort by (count, symbol): keys are distinct, so a key's rank is the number of smaller keys
+    if (tid < n) {
+        const uint32_t k = t.key[tid];
+        uint32_t r = 0;
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(t.key);
+        for (int j = 0; j < (n + 3) >> 2; ++j) {
+            const uint4 q = k4[j];
+            r += (q.x < k) + (q.y < k) + (q.z < k) + (q.w < k);
+        }
+        t.W[r] = k >> 8;
+        t.ord[r] = (uint8_t)k;
+    }
+    const int root = n - 2;
+    if (tid < n - 1) t.D[tid] = tid == root ? 0 : 1;
+    if (tid == root) t.P[root] = (uint16_t)root;
+    __syncthreads();
+    // (2) the merge is serial by nature; everybody else waits at the barrier
+    if (tid == 0) two_queue_merge(t.W, t.IW, t.P, n);
+    __syncthreads();
+    // depth of every internal node: pointer jumping (P <- P[P], D <- D + D[P]) until all point at the root
+    for (;;) {
+        const uint32_t pq = tid < n - 1 ? t.P[tid] : (uint32_t)root;
+        if (!__syncthreads_or(pq != (uint32_t)root)) break;
+        const uint32_t d = t.D[tid < n - 1 ? tid : root], pp = t.P[pq], dp = t.D[pq];
+        __syncthreads();
+        if (tid < n - 1) { t.P[tid] = (uint16_t)pp; t.D[tid] = (uint16_t)(d + dp); }
+    }
+    // (3) leaves per depth: an internal node at depth d-1 has two children at depth d, internal or leaf;
+    // depths beyond kL fold into kL
+    if (tid < n - 1) atomicAdd(&t.cntd[t.D[tid]], 1u);
+    __syncthreads();
+    if (tid >= 1) {
+        const uint32_t leaves = 2u * t.cntd[tid - 1] - t.cntd[tid];
+        if (leaves) atomicAdd(&t.num[min(tid, kL)], leaves);
+    }
+    __syncthreads();
+    // (4) Kraft repair, then the first canonical code of each length
+    if (tid == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int l = 1; l <= kL; ++l) total += t.num[l] << (kL - l);
+        while (total > (1u << kL)) {
+            t.num[kL]--;
+            for (int l = kL - 1; l >= 1; --l)
+                if (t.num[l]) { t.num[l]--; t.num[l + 1] += 2; break; }
+            --total;
+        }
+        uint32_t nx = 0, prev = 0;
+#pragma unroll
+        for (int l = 1; l <= kL; ++l) { nx = (nx + prev) << 1; t.next[l] = nx; prev = t.num[l]; }
+    }
+    __syncthreads();
+    // (5) lengths by sorted rank: the rarest symbols get the longest codes
+    if (tid < n) {
+        int l = kL;
+        uint32_t acc = t.num[kL];
+        while ((uint32_t)tid >= acc && l > 1) { --l; acc += t.num[l]; }
+        t.lenS[t.ord[tid]] = (uint8_t)l;
+    }
+    __syncthreads();
+    // canonical codes in (length, symbol) order: rank among the equal-length symbols below this one
+    const uint32_t l = t.lenS[tid];
+    const uint32_t m = __match_any_sync(0xFFFFFFFFu, l);
+    if ((m & lt) == 0) t.wcnt[warp][l] = __popc(m);
+    __syncthreads();
+    uint32_t e = 0;
+    if (l) {
+        uint32_t r = __popc(m & lt);
+#pragma unroll
+        for (int w = 0; w < kEncWarps; ++w) r += w < warp ? t.wcnt[w][l] : 0u;
+        e = (t.next[l] + r) | (l << 24);
+    }
+    tab[tid] = e;
+    nib[tid] = (uint8_t)l;
+    const uint32_t b = __reduce_add_sync(0xFFFFFFFFu, cnt * l);
+    if (lane == 0 && b) atomicAdd(&t.bits, b);
+    __syncthreads();
+    return t.bits;
+}
+
+// Stage-level entry (tests): tables from histograms in global memory through cta_table.
+__global__ void __launch_bounds__(kEncThreads) k_tables_cta(const uint16_t *__restrict__ hist, uint16_t *__restrict__ table,
+                                                          uint32_t *__restrict__ bits) {
+    __shared__ __align__(16) TabScratch t;
+    __shared__ uint32_t tab[256];
+    __shared__ uint8_t nib[256];
+    const int tid = threadIdx.x;
+    const uint64_t gb = blockIdx.x;
+    const uint32_t b = cta_table(hist[gb * 256 + tid], t, tab, nib, tid);
+    table[gb * 256 + tid] = (uint16_t)(((uint32_t)nib[tid] << 12) | (tab[tid] & 0xFFFu));
+    if (bits && tid == 0) bits[gb] = b;
+}
+
+void launch_tables_cta(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s) {
+    k_tables_cta<<<(unsigned)nblocks, kEncThreads, 0, s>>>(d_hist, d_table, d_bits);
+}
+
+// look-back status word: epoch (22 bits) | flag (2) | value (40 bits, words)
+constexpr unsigned long long kStA = 1ull << 40, kStP = 2ull << 40, kStVal = (1ull << 40) - 1;
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct FusedSmem {
+    uint32_t tile[kBH * kStagePitch];  // per row: residual words (word j of lane L at j*32 + L), then the packed row
+    union { uint32_t sh[kEncWarps][256]; TabScratch t; } u;
+    uint32_t tab[256];
+    uint8_t nib[256];
+    uint32_t rwc[kBH], rowoff[kBH], rbit0[kBH + 1];  // words per row, word offset of each row's tail, first bit of each row
+    uint32_t s_or[4], s_first, s_minw, s_used, s_size;
+    unsigned long long s_excl;
+    long long s_ticket;
+};
+
+template <int C, bool SG>
+__global__ void __launch_bounds__(kEncThreads, kFusedCtas)
+k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ streams, uint64_t capacity_words,
+         unsigned long long *__restrict__ dirE, unsigned long long *status, unsigned long long *ticket,
+         unsigned long long ticket_base, uint32_t epoch, uint32_t *err, PackMul pm) {
+    __shared__ __align__(16) FusedSmem sm;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t total = (uint64_t)g.n * g.nb;
+    const bool one = one_stream(g.flags), exact = (g.flags & FLIC_FLAG_EXACT) != 0;
+    const int hdrw = one ? kBlkHdrWords1 : kBlkHdrWords;
+    const unsigned long long ep = (unsigned long long)epoch << 42;
+    const bool fast = g.aligned16 != 0;
+    const uint32_t stile = (uint32_t)__cvta_generic_to_shared(sm.tile);
+
+    for (;;) {
+        if (tid == 0) sm.s_ticket = (long long)(atomicAdd(ticket, 1ull) - ticket_base);
+        {   // the previous block's copy-out has read the tile and the tables: the barrier below orders it
+            uint4 *z = reinterpret_cast<uint4 *>(&sm.u.sh[0][0]);
+#pragma unroll
+            for (int i = 0; i < kEncWarps * 256 / 4 / kEncThreads; ++i) z[tid + i * kEncThreads] = make_uint4(0, 0, 0, 0);
+        }
+        if (tid < 4) sm.s_or[tid] = 0;
+        __syncthreads();
+        const uint64_t gb = (uint64_t)sm.s_ticket;
+        if (gb >= total) break;
+        const BlockPos p = block_pos(g, gb);
+        const int nvl = C * max(0, min(4, (int)p.bwa - 4 * lane));  // real bytes of this lane in a real row
+
+        // ---- A. rows -> residuals -> tile + sub-histograms -------------------------------------------
+        {
+            uint32_t v[kBH / kEncWarps][C];
+            uint32_t upv[kBH / kEncWarps];
+            const uint8_t *row = pixels + (uint64_t)p.img * g.img_stride + (uint64_t)(p.y0 + warp) * g.pitch + (uint64_t)p.x0 * C;
+#pragma unroll
+            for (int q = 0; q < kBH / kEncWarps; ++q) {  // all loads first: four rows in flight per thread
+                const int r = warp + kEncWarps * q;
+                int nv;
+                upv[q] = 0;
+                if (r < (int)p.bha) {
+                    load_lane_pixels<C>(row, lane, (int)p.bwa, fast, v[q], &nv);
+                    if (lane == 0 && r > 0) upv[q] = up_pixel<C, SG>(row, g.pitch, fast);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < C; ++j) v[q][j] = 0;
+                }
+                row += kEncWarps * g.pitch;
+            }
+            uint32_t orw[C];
+#pragma unroll
+            for (int j = 0; j < C; ++j) orw[j] = 0;
+            char *my = reinterpret_cast<char *>(sm.u.sh[warp]);
+            uint32_t zero_rows = 0;
+#pragma unroll
+            for (int q = 0; q < kBH / kEncWarps; ++q) {
+                const int r = warp + kEncWarps * q;
+                if (r < (int)p.bha) {  // warp-uniform
+                    uint32_t res[C];
+                    lane_residuals<C, SG>(v[q], upv[q], lane, res);
+                    uint32_t *trow = sm.tile + r * kStagePitch + kStagePad + lane;
+#pragma unroll
+                    for (int j = 0; j < C; ++j) {
+                        trow[32 * j] = res[j];
+                        uint32_t x = res[j];
+                        if (q == 0 && j == 0 && tid == 0) {  // the block's first pixel: its residual is its value
+                            constexpr uint32_t fm = C == 4 ? 0xFFFFFFFFu : ((1u << (8 * (C & 3))) - 1u);
+                            sm.s_first = x & fm;
+                            x &= ~fm;
+                        }
+                        // bytes past the lane's last real pixel hold garbage differences: keep them out of the OR
+                        const int nb = min(4, max(0, nvl - 4 * j));
+                        const uint32_t vm = nb == 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+                        orw[C == 4 ? 0 : j] |= x & vm;
+                    }
+                    if (C == 4 && __all_sync(0xFFFFFFFFu, nvl == 4 * C && ((res[0] | res[1 % C] | res[2 % C] | res[3 % C]) & 0xFF000000u) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4 * C; ++j)
+                            if ((j & 3) != 3) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[j >> 2], j & 3)), 1u);
+                        ++zero_rows;  // an all-zero alpha row (opaque plane): counted once, not looked up
+                    } else if (nvl == 4 * C) {
+#pragma unroll
+                        for (int j = 0; j < 4 * C; ++j) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[j >> 2], j & 3)), 1u);
+                    } else if (nvl > 0) {
+#pragma unroll
+                        for (int j = 0; j < 4 * C; ++j)
+                            if (j < nvl) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[j >> 2], j & 3)), 1u);
+                    }
+                }
+            }
+            if (C == 4 && lane == 0 && zero_rows) atomicAdd(&sm.u.sh[warp][0], zero_rows * (uint32_t)kBW);
+            constexpr int NA = C == 4 ? 1 : C;
+#pragma unroll
+            for (int j = 0; j < NA; ++j) {
+                const uint32_t o = __reduce_or_sync(0xFFFFFFFFu, orw[j]);
+                if (lane == 0 && o) atomicOr(&sm.s_or[j], o);
+            }
+        }
+        __syncthreads();
+
+        // ---- B. this thread's symbol count; flat channels (FLP0 §2b) ----------------------------------
+        uint32_t cnt = 0, flatmask, flatvals;
+        {
+#pragma unroll
+            for (int k = 0; k < kEncWarps; ++k) cnt += sm.u.sh[k][tid];
+            uint32_t T;
+            if (C == 4) T = sm.s_or[0];
+            else if (C == 3) {  // word j byte b carries channel (4j + b) mod 3
+                const uint32_t a = sm.s_or[0], b = sm.s_or[1 % C], c = sm.s_or[2 % C];
+                T = (a | __byte_perm(b, 0u, 0x4102) | __byte_perm(c, 0u, 0x4021) | (a >> 24) |
+                     __byte_perm(b, 0u, 0x4434) | __byte_perm(c, 0u, 0x4344)) & 0x00FFFFFFu;
+            } else if (C == 2) { const uint32_t x = sm.s_or[0] | sm.s_or[1 % C]; T = (x | (x >> 16)) & 0xFFFFu; }
+            else { uint32_t x = sm.s_or[0]; x |= x >> 16; T = (x | (x >> 8)) & 0xFFu; }
+            auto nonzero_bytes = [](uint32_t x) { x |= x >> 4; x |= x >> 2; x |= x >> 1; return x & 0x01010101u; };
+            constexpr uint32_t chb = C == 4 ? 0x01010101u : ((1u << (8 * (C & 3))) - 1u) & 0x01010101u;
+            const uint32_t flatb = ~nonzero_bytes(T) & chb;  // bit 8*ch: channel ch is flat
+            const uint32_t first = sm.s_first, npix = p.bwa * p.bha;
+            if (tid == 0) cnt -= __popc(flatb) * (npix - 1u);
+            cnt -= __popc(~nonzero_bytes(first ^ ((uint32_t)tid * 0x01010101u)) & flatb);
+            flatmask = (flatb * 0x01020408u) >> 24;
+            flatvals = first & (flatb * 0xFFu);
+        }
+        __syncthreads();  // every thread has read the sub-histograms: the table scratch may overwrite them
+
+        // ---- C. code table ------------------------------------------------------------------------------
+        const uint32_t code_bits = cta_table(cnt, sm.u.t, sm.tab, sm.nib, tid);
+        uint32_t size = 0;  // words this block occupies in the stream (known now, except with EXACT)
+        if (one) size = (uint32_t)kBlkHdrWords1 + ((code_bits + 31u) >> 5);
+        else if (!exact) size = (uint32_t)kBlkHdrWords + (code_bits >> 5) + (code_bits ? p.bha : 0u);
+        if (!exact && tid == 0 && gb > 0) st_status(status + gb, ep | kStA | size);  // early: successors need not wait for the packing
+
+        // ---- D. pack the rows over the tile --------------------------------------------------------------
+        {
+            uint32_t skip[C];
+#pragma unroll
+            for (int j = 0; j < C; ++j) skip[j] = word_channel_bits<C>(flatmask, j);
+#pragma unroll 1
+            for (int q = 0; q < kBH / kEncWarps; ++q) {
+                const int r = warp + kEncWarps * q;
+                uint32_t *trow = sm.tile + r * kStagePitch + kStagePad;
+                const int nv = r < (int)p.bha ? nvl : 0;
+                uint32_t cur[C];
+#pragma unroll
+                for (int j = 0; j < C; ++j) cur[j] = nv ? trow[32 * j + lane] : 0u;
+                uint32_t qlo[C], qhi[C], ql[C], nbits = 0;
+                if (nv == 4 * C && flatmask == 0) {
+#pragma unroll
+                    for (int j = 0; j < C; ++j) { ql[j] = quad_of<true, 0>(cur[j], 4 * j, 4 * C, 0u, sm.tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+                } else if (nv == 4 * C && C == 4 && flatmask == 8u) {
+#pragma unroll
+                    for (int j = 0; j < C; ++j) { ql[j] = quad_of<true, 8>(cur[j], 4 * j, 4 * C, 8u, sm.tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < C; ++j) { ql[j] = quad_of<false, -1>(cur[j], 4 * j, nv, skip[j], sm.tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+                }
+                const uint32_t incl = warp_incl_scan(nbits, lane);
+                const uint32_t rowbits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const uint32_t rw = (rowbits + 31u) >> 5;
+                if (lane == 31) { sm.rwc[r] = rw; sm.rbit0[r] = rowbits; }
+                __syncwarp();  // all lanes hold their residuals: the row may be overwritten
+                // clear exactly the words the copy-out will read (one more with ONE_STREAM, whose funnel
+                // shifts look one word ahead)
+                for (uint32_t i = lane; i < rw + (one ? 1u : 0u); i += 32) trow[i] = 0u;
+                __syncwarp();
+                uint32_t nb = 0u - (8u * (stile + 4u * (uint32_t)(r * kStagePitch + kStagePad)) + (incl - nbits));
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    nb -= ql[j];
+                    const uint32_t a = ((31u - nb) >> 3) & ~3u;  // byte address one past the word the group ends in
+                    red_or_shared(a, -4, __funnelshift_l(0u, qlo[j], nb));
+                    red_or_shared(a, -8, __funnelshift_l(qlo[j], qhi[j], nb));
+                    if (__any_sync(0xFFFFFFFFu, ql[j] > 32u)) red_or_shared(a, -12, __funnelshift_l(qhi[j], 0u, nb));
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- E. size, position (decoupled look-back), directory ---------------------------------------------
+        if (warp == 0) {
+            const uint32_t wcount = sm.rwc[lane];
+            const uint32_t incl = warp_incl_scan(wcount, lane);
+            sm.rowoff[lane] = incl - wcount;
+            uint32_t mn = lane < (int)p.bha ? wcount : 0xFFFFFFFFu;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+            const uint32_t rb = sm.rbit0[lane];
+            const uint32_t bincl = warp_incl_scan(rb, lane);
+            __syncwarp();
+            sm.rbit0[lane] = bincl - rb;
+            if (lane == 31) sm.rbit0[kBH] = bincl;
+            uint32_t used = one ? (uint32_t)kBlkHdrWords1 + ((__shfl_sync(0xFFFFFFFFu, bincl, 31) + 31u) >> 5)
+                                : (uint32_t)kBlkHdrWords + __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (exact) size = used;
+            if (used > size || (one && used != size)) {  // cannot happen: a slot covers the rows' padding; one stream has none
+                if (lane == 0) atomicOr(err, kErrSlot);
+                used = 0xFFFFFFFFu;
+            }
+            // exclusive prefix of the sizes of all blocks before this one
+            unsigned long long excl = 0;
+            if (gb > 0) {
+                if (exact && lane == 0) st_status(status + gb, ep | kStA | size);
+                long long j = (long long)gb - 1 - lane;
+                for (;;) {
+                    unsigned long long v = 0;
+                    if (j >= 0) {
+                        do { v = ld_status(status + j); } while ((v >> 42) != epoch || (v & (kStA | kStP)) == 0);
+                    }
+                    const uint32_t pmask = __ballot_sync(0xFFFFFFFFu, j >= 0 && (v & kStP) != 0);
+                    const int stop = pmask ? __ffs(pmask) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
+                    unsigned long long c = (j >= 0 && lane <= stop) ? (v & kStVal) : 0ull;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        const uint32_t lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)c, d), hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(c >> 32), d);
+                        c += ((unsigned long long)hi << 32) | lo;
+                    }
+                    excl += c;
+                    if (pmask || j - (31 - lane) <= 0) break;  // found a prefix, or the window reached block 0 (uniform: lane 31's j)
+                    j -= 32;
+                }
+            }
+            if (lane == 0) {
+                st_status(status + gb, ep | kStP | ((excl + size) & kStVal));
+                dirE[gb] = excl;
+                if (gb + 1 == total) dirE[total] = excl + size;
+                sm.s_excl = excl;
+                sm.s_minw = mn;
+                sm.s_used = used;
+                sm.s_size = size;
+            }
+        }
+        __syncthreads();
+        size = sm.s_size;
+        const uint32_t used = sm.s_used;
+        const unsigned long long base = (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + sm.s_excl;
+        if (used == 0xFFFFFFFFu) continue;
+        if (base + size > capacity_words) {
+            if (tid == 0) atomicOr(err, kErrCapacity);
+            continue;
+        }
+
+        // ---- F. copy-out --------------------------------------------------------------------------------------
+        uint32_t *out = streams + base;
+        if (warp == 0) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v |= (uint32_t)sm.nib[8 * lane + k] << (4 * k);
+            out[lane] = v;
+        } else if (!one && warp == 1 && lane < kBH / 2) {
+            out[32 + lane] = sm.rwc[2 * lane] | (sm.rwc[2 * lane + 1] << 16);
+        } else if (warp == 2 && lane < 2) {
+            out[hdrw - 2 + lane] = lane ? flatvals : flatmask;
+        }
+        out += hdrw;
+        if (one) {
+            // FLP0 §8: the rows back to back, bit-exactly.  Output word m holds stream bits [32m, 32m + 32): find the
+            // row that bit 32m falls in, then OR in every row that overlaps the word (staged rows are zero past
+            // their last bit, one word beyond included).
+            const uint32_t nw = size - (uint32_t)kBlkHdrWords1;
+            for (uint32_t m = tid; m < nw; m += kEncThreads) {
+                const uint32_t b0 = 32u * m;
+                int r = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) r += (r + s < kBH && sm.rbit0[r + s] <= b0) ? s : 0;
+                uint32_t acc = 0;
+                for (; r < kBH && sm.rbit0[r] < b0 + 32u; ++r) {
+                    if (sm.rbit0[r + 1] <= b0 || sm.rbit0[r + 1] == sm.rbit0[r]) continue;  // an empty row
+                    const uint32_t *src = sm.tile + r * kStagePitch + kStagePad;
+                    const uint32_t s0 = sm.rbit0[r];
+                    if (s0 <= b0) {
+                        const uint32_t rel = b0 - s0;
+                        acc |= __funnelshift_l(src[(rel >> 5) + 1], src[rel >> 5], rel & 31u);
+                    } else {
+                        acc |= src[0] >> (s0 - b0);
+                    }
+                }
+                out[m] = acc;
+            }
+            continue;
+        }
+        for (uint32_t i = used + tid; i < size; i += kEncThreads) (out - hdrw)[i] = 0u;  // slack of the slot
+        const uint32_t minw = sm.s_minw, bha = p.bha, inter = minw * bha;
+        if (bha == (uint32_t)kBH) {  // thread = (k = warp, r = lane): i = k*32 + r = tid, then k += 8 per step
+            const uint32_t *src = sm.tile + lane * kStagePitch + kStagePad + warp;
+            uint32_t *dst = out + tid;
+            for (uint32_t k = warp; k < minw; k += kEncWarps, src += kEncWarps, dst += kEncThreads) *dst = *src;
+        } else {
+            for (uint32_t i = tid; i < inter; i += kEncThreads) {
+                const uint32_t k = i / bha, r = i - k * bha;
+                out[i] = sm.tile[r * kStagePitch + kStagePad + k];
+            }
+        }
+        {   // tails (a few words per row, back to back in row order): eight threads per row
+            const uint32_t r = tid >> 3, j = tid & 7;
+            if (r < bha) {
+                const uint32_t cntw = sm.rwc[r] - minw;
+                uint32_t *o = out + inter + (sm.rowoff[r] - r * minw);
+                const uint32_t *src = &sm.tile[r * kStagePitch + kStagePad + minw];
+                for (uint32_t i = j; i < cntw; i += 8) o[i] = src[i];
+            }
+        }
+    }
+}
+
+// Grid: resident CTAs only (the loop is persistent); correctness does not depend on co-residency, because a
+// CTA that has not started has not claimed a ticket, and tickets are what the look-back waits on.
+template <int C, bool SG>
+static unsigned fused_grid(uint64_t total) {
+    static int per_sm = 0, sms = 0;
+    if (!per_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode<C, SG>, kEncThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    const uint64_t cap = (uint64_t)sms * per_sm;
+    return (unsigned)(total < cap ? total : cap);
+}
+
+unsigned launch_encode_fused(const uint8_t *d_pixels, const Geo &g, uint32_t *d_streams, uint64_t capacity_words,
+                             unsigned long long *d_dirE, unsigned long long *d_status, unsigned long long *d_ticket,
+                             unsigned long long ticket_base, uint32_t epoch, uint32_t *d_err, cudaStream_t s) {
+    const uint64_t total = (uint64_t)g.n * g.nb;
+    const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) && g.c >= 3;
+    const PackMul pm = {1u << 8, 1u << 10, 1u << 18, 1u << 26};
+    unsigned grid = 0;
+#define FLIC_ENC(C, SG) \
+    (grid = fused_grid<C, SG>(total), \
+     k_encode<C, SG><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_streams, capacity_words, d_dirE, d_status, d_ticket, ticket_base, epoch, d_err, pm))
+    switch (g.c) {
+        case 1: FLIC_ENC(1, false); break;
+        case 2: FLIC_ENC(2, false); break;
+        case 3: if (sg) FLIC_ENC(3, true); else FLIC_ENC(3, false); break;
+        default: if (sg) FLIC_ENC(4, true); else FLIC_ENC(4, false); break;
+    }
+#undef FLIC_ENC
+    return grid;
 }
 
 }  // namespace flic

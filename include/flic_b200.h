@@ -36,6 +36,7 @@ extern "C" {
 #define FLIC_E_NO_DEVICE (-5)   /* no sm_100 device: there is no CPU fallback */
 #define FLIC_E_UNSUPPORTED (-6) /* valid FLP0 feature this build has no kernel for */
 #define FLIC_E_INTERNAL (-7)    /* device-side consistency check tripped */
+#define FLIC_E_BUSY (-8)        /* a submitted operation of the same kind has not been waited for */
 
 #define FLIC_BLOCK_W 128        /* pixels per block row   (one CTA / one decode warp per block) */
 #define FLIC_BLOCK_H 32         /* rows per block         (one decode lane per row sub-stream)  */
@@ -44,6 +45,17 @@ extern "C" {
 
 #define FLIC_PRED_LEFT 1u       /* flags bits 0-3: predictor id */
 #define FLIC_FLAG_SUBGREEN 0x10u
+/* Two optional stream layouts (round 2; both are modes of FLP0 v3 recorded in the header's flags byte,
+ * both exist to measure the engine on the PESSIMISTIC assumptions about a format it did not design):
+ *  ONE_STREAM  a block is ONE contiguous MSB-first bit stream (all rows back to back, padded to a word
+ *              once), with no per-row sub-streams and no row word counts: nothing in the stream tells a
+ *              decoder where a row starts, so parallel decode has to self-synchronise (k_decode_one).
+ *  EXACT       per-row sub-streams as usual, but a block occupies exactly the words it uses (slack 0):
+ *              its size is NOT known before it is packed, so the encoder places blocks with a
+ *              single-pass decoupled look-back over the packed sizes instead of precomputed slots. */
+#define FLIC_FLAG_ONE_STREAM 0x20u
+#define FLIC_FLAG_EXACT 0x40u
+#define FLIC_FLAGS_ALL 0x7Fu
 
 typedef struct flic_ctx flic_ctx;
 
@@ -58,6 +70,16 @@ void flic_destroy(flic_ctx *ctx);
 const char *flic_strerror(int code);
 const char *flic_last_error(const flic_ctx *ctx); /* detail of the last FLIC_E_CUDA / _INTERNAL */
 int flic_version(void);
+
+/* Options.  FLIC_OPT_ENCODER selects the encode path for plain FLP0 v3 streams: the fused single-pass
+ * kernel (default: pixels are read once, residuals never leave the SM) or the round-1 staged pipeline
+ * (five kernels with a residual plane in HBM; kept for A/B measurements).  Both produce identical bytes.
+ * FLIC_FLAG_ONE_STREAM / FLIC_FLAG_EXACT streams always take the fused kernel.  The environment variable
+ * FLIC_ENCODER=staged sets the same default at flic_create(). */
+#define FLIC_OPT_ENCODER 1
+#define FLIC_ENCODER_FUSED 0
+#define FLIC_ENCODER_STAGED 1
+int flic_set_option(flic_ctx *ctx, int option, int value);
 
 /* ---- size queries ------------------------------------------------------ */
 uint64_t flic_blocks_per_image(uint32_t w, uint32_t h);
@@ -84,15 +106,45 @@ int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams, const uint
 
 /* Synchronises `stream` and reports device-side error flags raised by the
  * kernels launched through ctx since the last check (capacity overrun,
- * corrupt directory, slot overrun). */
+ * corrupt directory, slot overrun, an image payload beyond 2^32 words).
+ *
+ * A context owns ONE encode workspace.  Encodes issued on different streams are
+ * ordered by an event (the later one waits for the earlier), so they are safe
+ * but do not overlap; use one context per concurrent encode. */
 int flic_check(flic_ctx *ctx, void *stream);
 
-/* ---- host-buffer batch API (H2D + kernels + D2H inside the call) ------- */
+/* ---- host-buffer batch API (H2D + kernels + D2H inside the call) -------
+ * The batch streams through double-buffered device staging on three CUDA streams (H2D, kernels, D2H).
+ * HOST MEMORY: the copies only overlap when the caller's buffers are page-locked.  Allocate them with
+ * cudaHostAlloc, or pin them ONCE with flic_host_register() (a cudaHostRegister wrapper for callers that do
+ * not link the CUDA runtime).  Pageable buffers of 1 MiB or more are pinned for the duration of each call
+ * (cudaHostRegister + cudaHostUnregister: correct, but it costs about 0.2 ms per MiB per call; set
+ * FLIC_NO_AUTOPIN=1 to skip it and take the driver's staged copies instead).
+ * flic_decode_batch accepts batches of mixed geometry: consecutive streams of one geometry are decoded
+ * together, pixels come out tightly packed in stream order. */
+int flic_host_register(void *p, uint64_t bytes);
+int flic_host_unregister(void *p);
 int flic_encode_batch(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n, uint32_t w, uint32_t h,
                       uint32_t c, uint32_t flags, uint8_t *h_streams, uint64_t capacity_bytes,
                       uint64_t *h_offsets /* n+1 */);
 int flic_decode_batch(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h_offsets,
                       uint32_t n, uint8_t *h_pixels, uint64_t pixels_capacity);
+
+/* Asynchronous forms: the same pipelines run on a worker thread of the context and the call returns at
+ * once; flic_wait(ctx, FLIC_OP_ENCODE / FLIC_OP_DECODE) joins it and returns its status.  Encode and decode
+ * own separate staging and streams, so ONE encode and ONE decode may be in flight together (FLIC_E_BUSY
+ * for a second of the same kind): an encode's stream download then overlaps a decode's stream upload and
+ * both directions of the PCIe link are busy.  The caller's buffers must stay valid, and must not be the
+ * other operation's output, until the wait returns.  Device-API calls on the same context must not be
+ * issued while an operation is in flight. */
+#define FLIC_OP_ENCODE 0
+#define FLIC_OP_DECODE 1
+int flic_encode_submit(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n, uint32_t w, uint32_t h,
+                       uint32_t c, uint32_t flags, uint8_t *h_streams, uint64_t capacity_bytes,
+                       uint64_t *h_offsets /* n+1 */);
+int flic_decode_submit(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h_offsets,
+                       uint32_t n, uint8_t *h_pixels, uint64_t pixels_capacity);
+int flic_wait(flic_ctx *ctx, int op);
 
 /* ---- host-only helpers -------------------------------------------------- */
 int flic_peek(const uint8_t *stream, uint64_t size, flic_image_info *info);
@@ -105,6 +157,31 @@ int flic_peek(const uint8_t *stream, uint64_t size, flic_image_info *info);
  * rebased.  Returns bytes written via *out_size. */
 int flic_splice_block_rows(const uint8_t *const *parts, const uint64_t *part_sizes, uint32_t k,
                            uint8_t *out, uint64_t out_capacity, uint64_t *out_size);
+
+/* Device-side splice, for parts that live in HBM (one GPU, or gathered over NVLink).
+ * flic_splice_block_rows_device: k part streams in device memory -> one stream at d_out (D2D copies of the
+ * directories and payloads + one kernel for the header and the directory rebase); reads the k 32-byte part
+ * headers back to the host first.  *out_size = bytes of the spliced stream.
+ *
+ * The multi-GPU form avoids the staging copy: after the all-gather of every part's (n_blocks,
+ * payload_words), flic_splice_plan() says where part i's directory entries (its first n_blocks[i] u32) and
+ * its payload land in the spliced stream; each rank sends them straight there (NCCL send/recv or P2P);
+ * flic_splice_finish_device() then writes the header, adds each part's payload base to its directory
+ * segment and appends the final entry.  flic_split_finish_device() is the inverse for decode: a buffer
+ * that received entries [b0, b0+nb] of a stream's directory at byte 32 and the payload words they span right
+ * behind them becomes the stand-alone stream of those block rows (header written, directory rebased). */
+#define FLIC_MAX_PARTS 64
+int flic_splice_block_rows_device(flic_ctx *ctx, const uint8_t *const *d_parts, const uint64_t *part_sizes,
+                                  uint32_t k, uint8_t *d_out, uint64_t out_capacity, uint64_t *out_size,
+                                  void *stream);
+int flic_splice_plan(const uint32_t *part_blocks, const uint32_t *part_payload_words, uint32_t k,
+                     uint64_t *dir_byte_off /* k */, uint64_t *payload_byte_off /* k */,
+                     uint64_t *total_bytes);
+int flic_splice_finish_device(flic_ctx *ctx, uint8_t *d_out, const uint32_t *part_blocks,
+                              const uint32_t *part_payload_words, uint32_t k, uint32_t w,
+                              uint32_t h_total, uint32_t c, uint32_t flags, void *stream);
+int flic_split_finish_device(flic_ctx *ctx, uint8_t *d_part, uint32_t w, uint32_t h_part, uint32_t c,
+                             uint32_t flags, void *stream);
 
 /* ---- stage-level entry points (used by the parity tests) ---------------- */
 /* Per-block residual histograms: d_hist[n_blocks_total][256] u16, flat channels left out;
@@ -125,7 +202,9 @@ int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t n_blocks_t
 #define FLIC_K_FINALIZE 3
 #define FLIC_K_DECODE 4
 #define FLIC_K_SLOTS 5
-#define FLIC_K_COUNT 6
+#define FLIC_K_ENCODE 6      /* the fused single-pass encoder */
+#define FLIC_K_DECODE_ONE 7  /* the self-synchronising decoder of FLIC_FLAG_ONE_STREAM streams */
+#define FLIC_K_COUNT 8
 /* When enabled, every kernel launched through ctx is bracketed by CUDA events
  * recorded on the launching stream.  flic_get_kernel_times() waits for the
  * recorded events, returns summed milliseconds and launch counts per kernel

@@ -203,7 +203,8 @@ static inline void bw_flush(bitw *b) {
 int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, uint32_t flags,
                     uint32_t bw, uint32_t bh, uint8_t *out, size_t out_capacity) {
     if (!pixels || !out || w == 0 || h == 0 || c < 1 || c > 4 || bw == 0 || bh == 0 || (bh & 1) ||
-        (flags & FLP0_FLAG_PRED_MASK) != FLP0_PRED_LEFT || (flags & ~0x1Fu) || bw * c * L / 32 > 65535u)
+        (flags & FLP0_FLAG_PRED_MASK) != FLP0_PRED_LEFT || (flags & ~(uint32_t)FLP0_FLAGS_ALL) || bw * c * L / 32 > 65535u ||
+        ((flags & FLP0_FLAG_ONE_STREAM) && (flags & FLP0_FLAG_EXACT)))
         return FLP0_E_ARG;
     if (out_capacity < flp0_max_stream_bytes(w, h, c, bw, bh)) return FLP0_E_CAPACITY;
 
@@ -237,6 +238,24 @@ int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, u
             put_u32(dir + 4 * (size_t)(by * nbx + bx), wpos);
             uint8_t *blk = payload + 4 * (size_t)wpos;
             for (int s = 0; s < 256; s += 2) blk[s >> 1] = (uint8_t)(len[s] | (len[s + 1] << 4));
+            if (flags & FLP0_FLAG_ONE_STREAM) {
+                /* flat words right after the nibbles, then one bit stream for the whole block */
+                uint8_t *fw1 = blk + 128;
+                put_u32(fw1, flat);
+                fw1[4] = fval[0]; fw1[5] = fval[1]; fw1[6] = fval[2]; fw1[7] = fval[3];
+                bitw b = { fw1 + 4 * FLATW, 0, 0, 0 };
+                for (uint32_t y = 0; y < bha; ++y) {
+                    const uint8_t *r = res + (size_t)y * rowsym;
+                    for (uint32_t i = 0; i < rowsym; ++i) {
+                        uint8_t l = len[r[i]];
+                        if ((flat >> (i % c)) & 1u) continue;
+                        if (l != FLP0_LEN_SOLE) bw_put(&b, code[r[i]], l);
+                    }
+                }
+                bw_flush(&b);
+                wpos += 32u + FLATW + b.words;
+                continue;
+            }
             uint8_t *rw = blk + 128;
             /* each row is bit-packed on its own ... */
             static _Thread_local uint32_t rwc[32768];
@@ -263,6 +282,7 @@ int64_t flp0_encode(const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t c, u
             for (int sy = 0; sy < 256; ++sy)
                 if (len[sy] >= 1 && len[sy] <= L) code_bits += (uint64_t)hist[sy] * len[sy];
             uint32_t slot = 32u + bh / 2u + FLATW + (uint32_t)(code_bits >> 5) + (code_bits ? bha : 0u);
+            if (flags & FLP0_FLAG_EXACT) slot = 32u + bh / 2u + FLATW + total; /* §FLP0.8: exactly the words used */
             uint8_t *fw = rw + 2 * bh; /* flat-channel words: mask, then the four values */
             put_u32(fw, flat);
             fw[4] = fval[0]; fw[5] = fval[1]; fw[6] = fval[2]; fw[7] = fval[3];
@@ -299,7 +319,8 @@ int flp0_peek(const uint8_t *s, size_t size, uint32_t *w, uint32_t *h, uint32_t 
     uint32_t W = get_u32(s + 8), H = get_u32(s + 12), C = s[6], F = s[7];
     uint32_t BW = get_u16(s + 16), BH = get_u16(s + 18), NB = get_u32(s + 20), PW = get_u32(s + 24);
     if (W == 0 || H == 0 || C < 1 || C > 4 || BW == 0 || BH == 0 || (BH & 1) ||
-        (F & FLP0_FLAG_PRED_MASK) != FLP0_PRED_LEFT || (F & ~0x1Fu))
+        (F & FLP0_FLAG_PRED_MASK) != FLP0_PRED_LEFT || (F & ~(uint32_t)FLP0_FLAGS_ALL) ||
+        ((F & FLP0_FLAG_ONE_STREAM) && (F & FLP0_FLAG_EXACT)))
         return FLP0_E_FORMAT;
     if ((uint64_t)ceil_div(W, BW) * ceil_div(H, BH) != NB) return FLP0_E_FORMAT;
     if ((uint64_t)FLP0_HEADER_BYTES + 4 * ((uint64_t)NB + 1) + 4 * (uint64_t)PW > size) return FLP0_E_FORMAT;
@@ -327,7 +348,8 @@ int flp0_decode(const uint8_t *s, size_t size, uint8_t *pixels, size_t cap) {
 
     for (uint32_t b = 0; b < nb; ++b) {
         uint32_t off = get_u32(dir + 4 * (size_t)b), end = get_u32(dir + 4 * (size_t)(b + 1));
-        if (off > end || end > pw || end - off < 32u + bh / 2u + FLATW) { free(lut); return FLP0_E_FORMAT; }
+        const int one = (flags & FLP0_FLAG_ONE_STREAM) != 0;
+        if (off > end || end > pw || end - off < (one ? 32u + FLATW : 32u + bh / 2u + FLATW)) { free(lut); return FLP0_E_FORMAT; }
         const uint8_t *blk = payload + 4 * (size_t)off;
         uint32_t x0 = (b % nbx) * bw, y0 = (b / nbx) * bh;
         uint32_t bwa = (w - x0 < bw) ? w - x0 : bw, bha = (h - y0 < bh) ? h - y0 : bh;
@@ -350,25 +372,31 @@ int flp0_decode(const uint8_t *s, size_t size, uint8_t *pixels, size_t cap) {
             }
         }
         const uint8_t *rw = blk + 128;
-        const uint8_t *fw = rw + 2 * bh;
+        const uint8_t *fw = one ? blk + 128 : rw + 2 * bh;
         uint32_t flat = get_u32(fw);
         if (flat >> c) { free(lut); return FLP0_E_FORMAT; }
         const uint8_t *body = fw + 4 * FLATW;
         uint32_t minw = 0xFFFFFFFFu, total = 0;
-        for (uint32_t y = 0; y < bh; ++y) {
+        /* §FLP0.8: one stream for the whole block — the reader state below carries over from row to row,
+         * and words past the block's extent read as zeros */
+        uint64_t acc1 = 0; int nacc1 = 0; uint32_t used1 = 0;
+        const uint32_t words1 = end - off - (32u + FLATW);
+        for (uint32_t y = 0; y < bh && !one; ++y) {
             uint32_t words = get_u16(rw + 2 * y);
             if (y >= bha && words) { free(lut); return FLP0_E_FORMAT; }
             if (y < bha && words < minw) minw = words;
             total += words;
         }
-        if (32u + bh / 2u + FLATW + total > end - off) { free(lut); return FLP0_E_FORMAT; }
+        if (!one && 32u + bh / 2u + FLATW + total > end - off) { free(lut); return FLP0_E_FORMAT; }
+        if (one) minw = 0;
         const uint8_t *tail = body + 4 * (size_t)minw * bha;
         for (uint32_t y = 0; y < bha; ++y) {
-            uint32_t words = get_u16(rw + 2 * y);
+            uint32_t words = one ? words1 : get_u16(rw + 2 * y);
             {
                 uint8_t *dst = pixels + ((size_t)(y0 + y) * w + x0) * c;
                 const uint8_t *up = dst - (size_t)w * c;
                 uint64_t acc = 0; int nacc = 0; uint32_t used = 0;
+                if (one) { acc = acc1; nacc = nacc1; used = used1; }
                 uint8_t prev[4] = {0, 0, 0, 0};
                 for (uint32_t x = 0; x < bwa; ++x) {
                     uint8_t t[4];
@@ -401,8 +429,9 @@ int flp0_decode(const uint8_t *s, size_t size, uint8_t *pixels, size_t cap) {
                     if ((flags & FLP0_FLAG_SUBGREEN) && c >= 3) { t[0] = (uint8_t)(t[0] + t[1]); t[2] = (uint8_t)(t[2] + t[1]); }
                     for (uint32_t ch = 0; ch < c; ++ch) dst[x * c + ch] = t[ch];
                 }
+                if (one) { acc1 = acc; nacc1 = nacc; used1 = used; }
             }
-            tail += 4 * (size_t)(words - minw);
+            if (!one) tail += 4 * (size_t)(words - minw);
         }
     }
     free(lut);

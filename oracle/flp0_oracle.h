@@ -35,6 +35,14 @@ extern "C" {
 #define FLP0_PRED_LEFT 1        /* x>0: left; x==0,y>0: up; (0,0): 0 — all within the block */
 #define FLP0_FLAG_PRED_MASK 0x0F
 #define FLP0_FLAG_SUBGREEN 0x10 /* R-=G, B-=G (mod 256) before prediction; channels >= 3 */
+/* DESIGN.md §FLP0.8 (round 2): two optional layouts, recorded in the header's flags byte.
+ * ONE_STREAM: the block header is 32 nibble words + 2 flat words, followed by ONE bit stream holding
+ *   all of the block's symbols in row-major order, zero-padded to a word once; no row word counts, no
+ *   row interleave, no slack.  EXACT: row sub-streams as in §FLP0.5-6, but the block occupies exactly
+ *   the words it uses (no slot slack, §FLP0.7 does not apply).  The two cannot be combined. */
+#define FLP0_FLAG_ONE_STREAM 0x20
+#define FLP0_FLAG_EXACT 0x40
+#define FLP0_FLAGS_ALL 0x7F
 
 /* error codes (negative returns) */
 #define FLP0_E_ARG (-1)

@@ -42,6 +42,9 @@ def alpha_ramp(w, h, seed):
     return img
 
 
+# flags: predictor 1 | 0x10 subtract-green | 0x20 one stream per block | 0x40 exact block sizes
+ALL_FLAGS = [0x01, 0x11, 0x21, 0x31, 0x41, 0x51]
+
 # (name, builder) — sizes chosen so the CPU model finishes each in well under a second
 SMALL = [
     ("c1_512x512x3", lambda: gradient(512, 512, 3, 1)),

@@ -20,9 +20,9 @@ import cases  # noqa: E402
 import oracle_binding  # noqa: E402
 
 orc = oracle_binding.Oracle(os.path.join(HERE, "..", "..", "oracle", "libflp0_oracle.so"))
-gold = {"format": "FLP0 v3 (flat channels), block 128x32, max code length 10", "sha256": {}}
+gold = {"format": "FLP0 v3 (flat channels; layouts: slots / 0x20 one stream / 0x40 exact), block 128x32, max code length 10", "sha256": {}}
 for name, build in cases.SMALL:
-    for flags in (0x01, 0x11):
+    for flags in cases.ALL_FLAGS:
         s = orc.encode(build(), flags)
         gold["sha256"][f"{name}@{flags:#04x}"] = {"bytes": int(s.size), "sha256": hashlib.sha256(s.tobytes()).hexdigest()}
 with open(os.path.join(HERE, "golden.json"), "w") as f:

@@ -21,9 +21,17 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+@pytest.fixture(params=["fused", "staged"])
+def encoder(request, codec):
+    """Both encode paths (the fused single-pass kernel and the round-1 staged pipeline) must emit the same bytes."""
+    codec.set_encoder(request.param)
+    yield request.param
+    codec.set_encoder("fused")
+
+
 @pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
 @pytest.mark.parametrize("flags", [0x01, 0x11])
-def test_stage_histograms_and_tables(codec, oracle, name, build, flags):
+def test_stage_histograms_and_tables(codec, oracle, encoder, name, build, flags):
     img = build()
     px = dev(img[None])
     nb = -(-img.shape[1] // 128) * -(-img.shape[0] // 32)
@@ -49,6 +57,17 @@ def test_stage_histograms_and_tables(codec, oracle, name, build, flags):
 
 @pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
 @pytest.mark.parametrize("flags", [0x01, 0x11])
+def test_staged_encoder_bytes(codec, oracle, name, build, flags):
+    codec.set_encoder("staged")
+    try:
+        img = build()
+        assert np.array_equal(codec.encode(img, flags), oracle.encode(img, flags))
+    finally:
+        codec.set_encoder("fused")
+
+
+@pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
+@pytest.mark.parametrize("flags", cases.ALL_FLAGS)
 def test_encode_bytes_and_decode_pixels(codec, oracle, name, build, flags):
     img = build()
     want = oracle.encode(img, flags)
@@ -192,6 +211,7 @@ def test_random_geometries(codec, oracle):
             x1 = w if rng.random() < 0.5 else max(1, w // 2)
             img = img.copy(); img[:, :x1, ch] = int(rng.integers(0, 256))
         flags = 0x11 if (c >= 3 and rng.random() < 0.5) else 0x01
+        flags |= int(rng.choice([0, 0, 0x20, 0x40]))   # layouts: slots, one stream per block, exact sizes
         want = oracle.encode(img, flags)
         got = codec.encode(img, flags)
         assert np.array_equal(got, want), (trial, w, h, c, flags, kind)
@@ -260,10 +280,12 @@ def test_c2_4k_rgba_roundtrip_and_model(codec, oracle):
     assert np.array_equal(got, oracle.encode(img[0]))  # 33 MB through the scalar model: ~0.3 s
 
 
-def test_c3_batch_slice_roundtrip(codec):
+def test_c3_batch_slice_roundtrip(codec, oracle):
     import flic_b200 as flic
     imgs = flic.workloads.make_batch("C3", n=48)
     streams, off = _roundtrip_device(codec, imgs)
+    # one full-size 1080p RGB image (1080 = 33.75 block rows: ragged bottom edge at a 5760-byte pitch) byte for byte
+    assert np.array_equal(streams[int(off[5]): int(off[6])].cpu().numpy(), oracle.encode(imgs[5]))
     # images repeat with period 8 -> so must their streams (a checksum-of-checksums style property)
     s = streams.cpu().numpy()
     for i in range(8, 48):
@@ -285,10 +307,12 @@ def test_4k_rgba_alpha_variants(codec, oracle):
     assert np.array_equal(got, oracle.encode(spot))
 
 
-def test_c5_uniform_noise_roundtrip(codec):
+def test_c5_uniform_noise_roundtrip(codec, oracle):
     import flic_b200 as flic
     imgs = flic.workloads.make_batch("C5", n=4)
-    _, off = _roundtrip_device(codec, imgs)
+    streams, off = _roundtrip_device(codec, imgs)
+    # one full-size noise image (every block at the worst-case code lengths) byte for byte against the model
+    assert np.array_equal(streams[int(off[2]): int(off[3])].cpu().numpy(), oracle.encode(imgs[2]))
     ratio = float(off[-1]) / imgs.size
     assert 1.0 < ratio < 1.03  # incompressible input: 8-bit codes + 1.2 % block headers + 0.8 % slot slack
 
@@ -298,3 +322,183 @@ def test_c4_strip_roundtrip(codec):
     import flic_b200 as flic
     img = flic.workloads.gradient_noise(16384, 2048, 4, 4)[None]
     _roundtrip_device(codec, img)
+
+
+# ---- round 2: layouts, fused encoder, async host API, device splice ----
+@pytest.mark.parametrize("flags", [0x21, 0x41])
+def test_layout_modes_full_size(codec, oracle, flags):
+    """ONE_STREAM (self-synchronising decoder) and EXACT (look-back over packed sizes) on full-size inputs:
+    a 4K RGBA gradient image, a 4K RGBA noise image (code lengths 7-9: the slowest to synchronise) and a
+    1080p RGB image, each byte-compared with the model and decoded back."""
+    import flic_b200 as flic
+    for imgs in (flic.workloads.make_batch("C2"), flic.workloads.make_batch("C5", n=1), flic.workloads.make_batch("C3", n=2)):
+        streams, off = _roundtrip_device(codec, imgs, flags)
+        got = streams[: int(off[1])].cpu().numpy()
+        assert np.array_equal(got, oracle.encode(imgs[0], flags))
+
+
+def test_one_stream_pathological_codes(codec, oracle):
+    """Inputs whose codes synchronise badly or not at all: two symbols with 1-bit codes, 2^k equiprobable symbols
+    (fixed-length codes never re-synchronise: the correction has to travel thread by thread), a single symbol."""
+    rng = np.random.default_rng(5)
+    h, w = 64, 256
+    imgs = []
+    for nsym in (1, 2, 4, 16, 256):
+        steps = rng.integers(0, nsym, size=(h, w, 1)).astype(np.uint8)
+        imgs.append(np.cumsum(steps, axis=1).astype(np.uint8))          # residuals uniform over nsym values
+    for img in imgs:
+        for c in (1, 3):
+            im = np.repeat(img, c, axis=2) if c > 1 else img
+            want = oracle.encode(im, 0x21)
+            got = codec.encode(im, 0x21)
+            assert np.array_equal(got, want)
+            assert np.array_equal(codec.decode(got), im)
+
+
+def test_decode_rejects_mismatched_geometry(codec, oracle):
+    """a stream of another channel count / colour transform / layout must not decode into plausible
+    garbage when the caller passes the wrong geometry to the device API."""
+    import flic_b200 as flic
+    img = cases.gradient(256, 64, 4, 50)
+    s = codec.encode(img, 0x11)
+    d_s, d_o = dev(s), torch.tensor([0, s.size], dtype=torch.int64, device="cuda")
+    for shape, flags in (((1, 64, 256, 4), 0x01), ((1, 64, 256, 4), 0x31), ((1, 64, 341, 3), 0x11), ((1, 32, 256, 4), 0x11)):
+        out = torch.zeros(shape, dtype=torch.uint8, device="cuda")
+        codec.decode_batch_device(d_s, d_o, out, flags)
+        with pytest.raises(flic.FlicError) as e:
+            codec.check()
+        assert e.value.code == -3, (shape, flags)
+    out = torch.zeros((1, 64, 256, 4), dtype=torch.uint8, device="cuda")
+    codec.decode_batch_device(d_s, d_o, out, 0x51)   # EXACT is an encoder-side property: same decode
+    codec.check()
+    assert np.array_equal(out.cpu().numpy()[0], img)
+
+
+def test_mixed_geometry_batch(codec, oracle):
+    """The host decode API takes batches of mixed geometry (runs of equal geometry decode together)."""
+    imgs = [cases.gradient(300, 70, 3, 1), cases.gradient(300, 70, 3, 2), cases.gradient(256, 64, 4, 3),
+            cases.noise(129, 65, 3, 4), cases.gradient(300, 70, 3, 5)]
+    flags = [0x01, 0x41, 0x21, 0x11, 0x01]   # the first two differ only in EXACT: one run
+    streams = [codec.encode(im, f) for im, f in zip(imgs, flags)]
+    off = np.concatenate([[0], np.cumsum([s.size for s in streams])]).astype(np.uint64)
+    out = np.zeros(sum(im.size for im in imgs), dtype=np.uint8)
+    codec.decode_batch(np.concatenate(streams), off, out=out)
+    pos = 0
+    for im in imgs:
+        assert np.array_equal(out[pos: pos + im.size].reshape(im.shape), im)
+        pos += im.size
+
+
+def test_submit_wait_overlap(codec, oracle):
+    """flic_encode_submit / flic_decode_submit / flic_wait: one encode and one decode in flight together on one
+    context, on pinned buffers; a second submit of the same kind is refused with FLIC_E_BUSY."""
+    import flic_b200 as flic
+    a = np.stack([cases.gradient(640, 200, 4, 300 + s) for s in range(6)])
+    b = np.stack([cases.noise(640, 200, 4, 400 + s) for s in range(6)])
+    pin = lambda x: torch.from_numpy(x).pin_memory().numpy()
+    a, b = pin(a), pin(b)
+    sb, ob = codec.encode_batch(b)
+    sb, ob = pin(sb.copy()), ob.copy()
+    out_b = pin(np.zeros_like(b))
+    cap = a.shape[0] * flic.max_stream_bytes(640, 200, 4)
+    out_a, off_a = pin(np.zeros(cap, np.uint8)), np.zeros(a.shape[0] + 1, np.uint64)
+    codec.encode_submit(a, out=out_a, offsets=off_a)
+    codec.decode_submit(sb, ob, out_b)
+    with pytest.raises(flic.FlicError) as e:
+        codec.encode_submit(a, out=out_a, offsets=off_a)
+    assert e.value.code == -8
+    codec.wait(flic.OP_DECODE)
+    codec.wait(flic.OP_ENCODE)
+    assert np.array_equal(out_b, b)
+    want = np.concatenate([oracle.encode(im) for im in a])
+    assert off_a[-1] == want.size and np.array_equal(out_a[: want.size], want)
+    with pytest.raises(flic.FlicError):
+        codec.wait(flic.OP_ENCODE)   # nothing in flight
+
+
+def test_pageable_and_pinned_host_buffers(codec, oracle, monkeypatch):
+    """Pageable caller buffers are pinned for the call (>= 1 MiB) or copied through the driver's staging; both
+    give the same bytes as pinned ones."""
+    imgs = np.stack([cases.gradient(1024, 300, 4, 500 + s) for s in range(3)])   # 3.7 MB: above the auto-pin threshold
+    want = np.concatenate([oracle.encode(im) for im in imgs])
+    s1, o1 = codec.encode_batch(imgs)
+    assert np.array_equal(s1, want)
+    monkeypatch.setenv("FLIC_NO_AUTOPIN", "1")
+    s2, o2 = codec.encode_batch(imgs)
+    assert np.array_equal(s2, want) and np.array_equal(o1, o2)
+    pinned = torch.from_numpy(imgs).pin_memory().numpy()
+    s3, _ = codec.encode_batch(pinned)
+    assert np.array_equal(s3, want)
+    assert np.array_equal(codec.decode_batch(s3, o1), imgs)
+
+
+@pytest.mark.parametrize("flags", [0x01, 0x21, 0x41])
+def test_device_splice_and_split(codec, oracle, flags):
+    """The C4 path on one GPU: block-row parts spliced on the device (D2D copies + one kernel) equal the encode of
+    the whole image; the plan/finish pair used across GPUs gives the same bytes; and the inverse (a run of block
+    rows cut out of the whole stream) decodes to those rows."""
+    import flic_b200 as flic
+    img = cases.gradient(700, 200, 4, 43)
+    whole = codec.encode(img, flags)
+    cuts = [(0, 96), (96, 160), (160, 200)]
+    parts = [codec.encode(img[a:b], flags) for a, b in cuts]
+    d_parts = [dev(p) for p in parts]
+    out = torch.zeros(whole.size + 64, dtype=torch.uint8, device="cuda")
+    n = codec.splice_block_rows_device(d_parts, out)
+    codec.check()
+    assert n == whole.size and np.array_equal(out[:n].cpu().numpy(), whole)
+    assert np.array_equal(flic.splice_block_rows(parts), whole)
+    # plan + finish: what every rank does after the all-gather of (n_blocks, payload_words)
+    infos = [flic.peek(p) for p in parts]
+    nbs, pws = [i["n_blocks"] for i in infos], [i["payload_words"] for i in infos]
+    doff, poff, total = flic.splice_plan(nbs, pws)
+    assert total == whole.size
+    out2 = torch.zeros(total, dtype=torch.uint8, device="cuda")
+    for p, nb, pw, do, po in zip(d_parts, nbs, pws, doff, poff):
+        out2[do: do + 4 * nb] = p[32: 32 + 4 * nb]
+        out2[po: po + 4 * pw] = p[32 + 4 * (nb + 1): 32 + 4 * (nb + 1) + 4 * pw]
+    codec.splice_finish_device(out2, nbs, pws, 700, 200, 4, flags)
+    codec.check()
+    assert np.array_equal(out2.cpu().numpy(), whole)
+    # split: block rows 3..4 (pixel rows 96..160) cut out of the whole stream
+    nbx = -(-700 // 128)
+    d_whole = dev(whole)
+    dirw = np.frombuffer(whole[32: 32 + 4 * (sum(nbs) + 1)].tobytes(), np.uint32)
+    b0, b1 = 3 * nbx, 5 * nbx
+    w0, w1 = int(dirw[b0]), int(dirw[b1])
+    part = torch.zeros(32 + 4 * (b1 - b0 + 1) + 4 * (w1 - w0), dtype=torch.uint8, device="cuda")
+    part[32: 32 + 4 * (b1 - b0 + 1)] = d_whole[32 + 4 * b0: 32 + 4 * (b1 + 1)]
+    pay0 = 32 + 4 * (sum(nbs) + 1)
+    part[32 + 4 * (b1 - b0 + 1):] = d_whole[pay0 + 4 * w0: pay0 + 4 * w1]
+    codec.split_finish_device(part, 700, 64, 4, flags)
+    codec.check()
+    assert np.array_equal(part.cpu().numpy(), parts[1])
+    assert np.array_equal(codec.decode(part.cpu().numpy()), img[96:160])
+
+
+def test_offsets_beyond_4gib(codec):
+    """BASELINE config 3's shape at its full size on one GPU — 1024 x 1080p RGB, 6.4 GB of pixels — with half of the
+    images noise, so that the streams total more than 4 GiB: u64 stream offsets, u32 directories per image."""
+    import flic_b200 as flic
+    n, h, w, c = 1024, 1080, 1920, 3
+    uniq = torch.cat([dev(flic.workloads.make_batch("C3", n=4)),
+                      dev(np.stack([flic.workloads.uniform_noise(w, h, c, 9000 + i) for i in range(4)]))])
+    px = uniq.repeat(n // 8, 1, 1, 1)
+    cap = n * int(codec.lib.flic_max_stream_bytes(w, h, c))
+    streams = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    codec.encode_batch_device(px, streams, off)
+    codec.check()
+    o = off.cpu().numpy()
+    sizes = np.diff(o)
+    assert (sizes[8:] == sizes[:-8]).all()
+    assert int(o[-1]) > (1 << 32) + (1 << 28)   # the last ~100 streams start beyond the 32-bit byte range
+    out = torch.empty_like(px)
+    codec.decode_batch_device(streams, off, out)
+    codec.check()
+    assert torch.equal(out[-8:], uniq) and torch.equal(out[512:520], uniq)
+    # the same bytes wherever an image sits in the batch, also past 4 GiB
+    for i in (3, 6):
+        a, b = int(o[i]), int(o[i + 1])
+        a2, b2 = int(o[1016 + i]), int(o[1016 + i + 1])
+        assert a2 > (1 << 32) and torch.equal(streams[a:b], streams[a2:b2])

@@ -13,7 +13,7 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
 @pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
-@pytest.mark.parametrize("flags", [0x01, 0x11])
+@pytest.mark.parametrize("flags", cases.ALL_FLAGS)
 def test_roundtrip(oracle, name, build, flags):
     img = build()
     s = oracle.encode(img, flags)
@@ -106,7 +106,8 @@ def test_canonical_codes_prefix_free(oracle):
 def test_errors(oracle):
     img = cases.gradient(64, 64, 3, 1)
     assert oracle.encode_rc(img, flags=0x02) == -1           # unknown predictor
-    assert oracle.encode_rc(img, flags=0x21) == -1           # reserved flag bit
+    assert oracle.encode_rc(img, flags=0x81) == -1           # reserved flag bit
+    assert oracle.encode_rc(img, flags=0x61) == -1           # ONE_STREAM and EXACT cannot be combined
     assert oracle.encode_rc(img, cap=100) == -2              # capacity
     s = oracle.encode(img)
     assert oracle.decode_rc(s[:20], img.shape) == -3         # truncated header
@@ -127,3 +128,24 @@ def test_blocks_are_independent(oracle):
     nb_t = int(np.frombuffer(top[20:24], np.uint32)[0]); nb_b = int(np.frombuffer(bot[20:24], np.uint32)[0])
     pay = lambda s, nb: s[32 + 4 * (nb + 1):]
     assert np.array_equal(np.concatenate([pay(top, nb_t), pay(bot, nb_b)]), pay(full, nb_t + nb_b))
+
+
+def test_layout_modes(oracle):
+    """FLP0 §8: EXACT drops the slot slack and nothing else; ONE_STREAM drops the row word counts, the row
+    padding and the slack.  All three layouts carry the same symbols with the same code tables."""
+    img = cases.gradient(300, 100, 3, 31)
+    slot, exact, one = oracle.encode(img, 0x01), oracle.encode(img, 0x41), oracle.encode(img, 0x21)
+    assert one.size < exact.size < slot.size
+    nb = int(np.frombuffer(slot[20:24], np.uint32)[0])
+    d = lambda s: np.frombuffer(s[32:32 + 4 * (nb + 1)].tobytes(), np.uint32).astype(np.int64)
+    ds, de, do = d(slot), d(exact), d(one)
+    pay = lambda s: np.frombuffer(s[32 + 4 * (nb + 1):].tobytes(), np.uint32)
+    for b in range(nb):
+        bs, be, bo = pay(slot)[ds[b]:ds[b + 1]], pay(exact)[de[b]:de[b + 1]], pay(one)[do[b]:do[b + 1]]
+        assert np.array_equal(bs[:32], be[:32]) and np.array_equal(bs[:32], bo[:32])      # length nibbles
+        assert np.array_equal(bs[:be.size], be) and not bs[be.size:].any()                # slot = exact + zero slack
+        rows = np.frombuffer(be[32:48].tobytes(), np.uint16).astype(np.int64)
+        assert be.size == 50 + rows.sum()
+        assert np.array_equal(be[48:50], bo[32:34])                                       # flat words
+        assert 0 <= rows.sum() - (bo.size - 34) <= 32                                     # at most one pad word per row saved
+    assert int(slot[7]) == 0x01 and int(exact[7]) == 0x41 and int(one[7]) == 0x21        # the header says which
