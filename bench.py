@@ -2,17 +2,22 @@
 """bench.py — raw-pixel GB/s of the encode+decode hot path (BASELINE.json `metric`).
 
 A step = one encode pass + one decode pass over one batch of synthetic images.
-  value : whole-job raw-pixel GB/s, inputs resident in HBM, CUDA-event timed.
-  e2e   : the same metric through the host-buffer C-ABI calls (pinned host memory in, host
-          memory out; H2D and D2H inside the timed region).
-  roofline / kernels : per-kernel CUDA-event durations from the library's timing hook,
-          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline : the scalar CPU model of the same provisional format on the host cores.
+  value     : whole-job raw-pixel GB/s, inputs resident in HBM, CUDA-event timed, max over ranks.
+  e2e       : the same metric through the host-buffer C-ABI calls on PINNED host buffers (H2D and D2H inside
+              the timed region); encode of step k+1 and decode of step k are in flight together
+              (flic_encode_submit / flic_decode_submit / flic_wait), so both directions of the link are busy.
+  roofline  : frac = min(encode path, decode path) of (1 + r) * N bytes per pass against the measured HBM copy
+              bandwidth in MEASURED_PEAKS.json; per-kernel CUDA-event durations from the library's timing hook.
+  secondary : the other BASELINE.json configs, driver-timed in the same run: C3 (1024 x 1080p RGB, STRONG scaling:
+              the fixed batch is split over the ranks), C5 (4K RGBA uniform noise, weak), C4 (ONE 16384^2 RGBA image
+              split by block rows over the ranks, all-gather + NVLink gather + splice INSIDE the timed region), and
+              the two pessimistic stream layouts on the main workload (ONE_STREAM, EXACT).
+  cpu_model : the scalar CPU model of the same provisional format on the host cores.
 
-LICENSING GATE: the reference may not be built, run or restated (LICENSING.md), so
-`--impl reference` times the only CPU implementation of this path that exists here: the
-scalar C model of the provisional FLP0 format in oracle/ (kind "port"), which is NOT the
-reference.
+LICENSING GATE: the reference may not be built, run or restated (LICENSING.md), and there is no Rust toolchain in
+the image, so the reference's own CPU implementation cannot be timed: `cpu_baseline` says "unavailable" and
+`--impl reference` prints {"impl": "reference", "unavailable": ...}.  The CPU number this script does measure is
+the scalar C model of the provisional FLP0 format (oracle/), reported as `cpu_model` — it is NOT the reference.
 """
 import argparse
 import json
@@ -30,6 +35,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "raw_pixel_GBps_encode_plus_decode"
 GATE = ("licensing gate: reference README reserves all use, no licence file; BASELINE.json north_star forbids "
         "building/running/restating it until cleared (LICENSING.md); no Rust toolchain in the image either")
+FORMAT = "FLP0 v3 (provisional; NOT the reference bitstream — licensing gate)"
+DISTINCT = 8  # images synthesised per workload; the rest of a batch cycles through them (8 x 33 MB still exceeds L2)
 
 # workload name -> (config id, images per GPU per step)
 WORKLOADS = {
@@ -37,7 +44,7 @@ WORKLOADS = {
     "C2x8": ("C2", 8),    # same geometry, 265 MB/step: short enough to profile under ncu, still > L2
     "C2Ax64": ("C2A", 64),  # the same batch with a gradient alpha plane (no flat channel: four symbols per pixel)
     "C1": ("C1", 1), "C2": ("C2", 1), "C3": ("C3", 128), "C4": ("C4", 1), "C5": ("C5", 64),
-    "C3full": ("C3", 1024),  # configs[2] at its full size on ONE GPU: 6.4 GB raw per step, > 4 GiB of stream offsets
+    "C3full": ("C3", 1024),  # configs[2] at its full size on ONE GPU: 6.4 GB raw per step
 }
 
 
@@ -111,150 +118,309 @@ def cpu_model_roundtrip(batch, seconds=20.0):
         res = list(ex.map(one, idx))
     dt = time.perf_counter() - t0
     assert all(ok for _, ok in res)
-    return {"value": k * per_img / dt / 1e9, "unit": "GB/s", "cores": min(cores, k),
-            "kind": "port",
+    return {"value": k * per_img / dt / 1e9, "unit": "GB/s", "cores": min(cores, k), "kind": "flp0-model",
             "sample": f"{k} images of {batch.shape[2]}x{batch.shape[1]}x{batch.shape[3]} encode+decode, "
                       f"{min(cores, k)} threads, {dt:.1f} s; scalar C model of FLP0 (oracle/), NOT the gated reference"}
 
 
-def run_c4_split(args):
-    """Config C4: ONE 16384x16384 RGBA8 image split by block rows across the ranks (strong scaling).
-    Each rank encodes + decodes its rows; the only collective on the data path is the all-gather of
-    one int64 byte count per rank, which is what lets every rank place its part in the spliced stream.
-    Untimed afterwards: the parts are gathered, spliced on the host (flic_splice_block_rows) and the
-    spliced stream is decoded on rank 0 against the gathered pixels."""
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import flic_b200
+def bind_to_gpu_numa(index):
+    """Pin this process's threads to the CPUs of the NUMA node the GPU hangs off, BEFORE the pinned buffers are
+    allocated (first touch then places them on that node), so H2D/D2H do not cross the socket interconnect.
+    Returns a short description; a no-op where the box exposes one node or hides the topology."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(os.path.join(path, "numa_node")).read())
+        cpus = open(os.path.join(path, "local_cpulist")).read().strip()
+        allowed = os.sched_getaffinity(0)
+        want = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            want.update(range(int(a), int(b or a) + 1))
+        want &= allowed
+        if node < 0 or not want or want == allowed:
+            return f"numa node {node}: no binding needed", None
+        os.sched_setaffinity(0, want)
+        return f"bound to numa node {node} ({len(want)} cpus)", allowed
+    except Exception as e:  # containers often hide /sys topology
+        return f"not bound ({type(e).__name__})", None
 
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    flic_b200.build_library()
-    codec = flic_b200.Codec(local)
+
+class Dist:
+    """Thin wrapper so single-GPU runs need no process group."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank, self.world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def sum(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def device_roundtrip(D, codec, px, flags, steps, warmup, kernel_times=False):
+    """Encode + decode of the CUDA tensor px [n,h,w,c], inputs resident in HBM.  Per-step CUDA events on the
+    launching stream; the L2 is flushed between steps when a step's pixels would fit in it.  Returns a dict with
+    max-over-ranks encode/decode ms per step, this rank's compressed bytes, kernel times and launch count."""
+    torch = D.torch
+    n, h, w, c = px.shape
+    raw = px.numel()
+    import flic_b200
+    cap = n * flic_b200.max_stream_bytes(w, h, c)
+    streams = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    out = torch.empty_like(px)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if raw < (512 << 20) else None
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(warmup):
+        codec.encode_batch_device(px, streams, off, flags, st)
+        codec.decode_batch_device(streams, off, out, flags, st)
+    codec.check(st)
+    assert torch.equal(out, px), "round trip is not lossless"
+    comp = int(off[-1].item())
+    if kernel_times:
+        codec.kernel_times()
+        codec.set_kernel_timing(True)
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(steps)]
+    launches0 = codec.launches
+    D.barrier()
+    for a, m, b in ev:
+        if flush is not None:
+            flush.fill_(1)
+        a.record()
+        codec.encode_batch_device(px, streams, off, flags, st)
+        m.record()
+        codec.decode_batch_device(streams, off, out, flags, st)
+        b.record()
+    D.barrier()
+    launches = codec.launches - launches0
+    kt = None
+    if kernel_times:
+        codec.set_kernel_timing(False)
+        kt = codec.kernel_times()
+    codec.check(st)
+    enc = sum(a.elapsed_time(m) for a, m, _ in ev) / steps
+    dec = sum(m.elapsed_time(b) for _, m, b in ev) / steps
+    tot, enc, dec = D.max([enc + dec, enc, dec])
+    del streams, out, flush
+    return {"ms": tot, "enc_ms": enc, "dec_ms": dec, "comp": comp, "raw": raw, "kernels": kt, "launches": launches,
+            "l2": "inputs_exceed_l2" if raw >= (512 << 20) else "l2_flushed_between_steps"}
+
+
+def secondary_lines(D, codec, args, hbm):
+    """The other BASELINE.json configs, device-resident, few steps each (the whole default run stays within minutes)."""
+    import flic_b200
+    torch = D.torch
+    sh, wl = flic_b200.sharding, flic_b200.workloads
+    K, W = max(3, min(args.steps, 5)), 3
+    out = {}
+
+    def line(res, total_raw, extra):
+        d = {"value_GBps": round(total_raw / (res["ms"] * 1e-3) / 1e9, 2),
+             "encode_GBps": round(total_raw / (res["enc_ms"] * 1e-3) / 1e9, 2),
+             "decode_GBps": round(total_raw / (res["dec_ms"] * 1e-3) / 1e9, 2), "ms_per_step": round(res["ms"], 4),
+             "steps": K, "l2": res["l2"]}
+        d.update(extra)
+        return d
+
+    def fracs(res):
+        alg = (res["raw"] + res["comp"]) / 1e9
+        return {"compressed_ratio": round(res["comp"] / res["raw"], 4),
+                "encode_path_frac": round(alg / (res["enc_ms"] * 1e-3) / hbm, 4),
+                "decode_path_frac": round(alg / (res["dec_ms"] * 1e-3) / hbm, 4)}
+
+    # C3: the FIXED batch of 1024 x 1080p RGB split over the ranks (strong scaling)
+    lo, hi = sh.batch_slice(1024, D.rank, D.world)
+    uniq = torch.from_numpy(wl.make_batch("C3", n=DISTINCT)).cuda()
+    px = uniq[torch.arange(lo, hi, device="cuda") % DISTINCT]
+    res = device_roundtrip(D, codec, px, args.flags, K, W)
+    out["C3_1024x1080p_rgb"] = line(res, 1024 * uniq[0].numel(), {"scaling": "strong", "images_per_rank": hi - lo,
+                                                                   "distinct_images": DISTINCT, **fracs(res)})
+    del px, uniq
+    # C5: 64 x 4K RGBA uniform noise per rank (weak), the worst case for code lengths and for decode
+    uniq = torch.from_numpy(wl.make_batch("C5", n=DISTINCT)).cuda()
+    px = uniq[torch.arange(64, device="cuda") % DISTINCT]
+    res = device_roundtrip(D, codec, px, args.flags, K, W)
+    out["C5_64x4k_rgba_noise"] = line(res, D.world * px.numel(), {"scaling": "weak", "images_per_rank": 64,
+                                                                  "distinct_images": DISTINCT, **fracs(res)})
+    del px, uniq
+    # the two pessimistic layouts on the main workload (VERDICT r1 items 2 and 3)
+    uniq = torch.from_numpy(wl.make_batch("C2", n=DISTINCT)).cuda()
+    px = uniq[torch.arange(64, device="cuda") % DISTINCT]
+    for name, fl in (("C2x64_one_stream_per_block", 0x20), ("C2x64_exact_sizes_lookback", 0x40)):
+        res = device_roundtrip(D, codec, px, (args.flags & 0x1F) | fl, K, W)
+        out[name] = line(res, D.world * px.numel(), {"scaling": "weak", "flags": (args.flags & 0x1F) | fl, **fracs(res)})
+    del px, uniq
+    torch.cuda.empty_cache()
+    out["C4_16384sq_rgba_split"] = c4_split(D, codec, args, K, W)
+    return out
+
+
+def synth_rows_cuda(torch, w, h, c, seed, y0, y1):
+    """Rows [y0, y1) of a w x h gradient+noise RGBA image, synthesised on the GPU (a 1 GiB image takes the host
+    half a minute): same recipe as workloads.gradient_noise (diagonal ramp + N(0, 4) noise, opaque alpha), torch's
+    generator instead of numpy's, seeded per 32-row band so any rank can make exactly its rows."""
+    rows = torch.empty((y1 - y0, w, c), dtype=torch.uint8, device="cuda")
+    x = torch.arange(w, dtype=torch.float32, device="cuda")[None, :, None]
+    g = torch.Generator(device="cuda")
+    for b0 in range(y0 - y0 % 32, y1, 32):
+        lo, hi = max(b0, y0), min(b0 + 32, y1, h)
+        if hi <= lo:
+            continue
+        g.manual_seed(seed * 1000003 + b0 // 32)
+        noise = torch.randn((32, w, min(c, 3)), generator=g, device="cuda") * 4.0
+        y = torch.arange(lo, hi, dtype=torch.float32, device="cuda")[:, None, None]
+        ramp = 255.0 * (x + y) / max(w + h - 2, 1)
+        base = torch.cat([ramp, 255.0 - ramp, ramp], dim=2)[..., : min(c, 3)]
+        rows[lo - y0: hi - y0, :, : min(c, 3)] = (base + noise[lo - b0: hi - b0]).clamp_(0, 255).to(torch.uint8)
+        if c == 4:
+            rows[lo - y0: hi - y0, :, 3] = 255
+    return rows
+
+
+def c4_split(D, codec, args, K, W):
+    """Config C4: ONE 16384x16384 RGBA8 image split by block rows over the ranks (strong scaling).  Timed region of a
+    step: every rank encodes its rows; all-gather of (n_blocks, payload_words); payloads and directory entries travel
+    by NCCL send/recv over NVLink straight into the spliced stream on rank 0; one kernel writes the header and
+    rebases the directory; then the inverse: rank 0 cuts the stream at block-row boundaries, sends the parts, every
+    rank finishes its part stream and decodes its rows.  Verified: spliced stream == the stream one GPU makes of
+    rows it is given (same bytes per block, checked through decode), decoded rows == input rows on every rank."""
+    import flic_b200
+    torch = D.torch
     _, w, h, c, _, seed = flic_b200.workloads.CONFIGS["C4"]
     if args.c4_height:
         h = args.c4_height
-    y0, y1 = flic_b200.sharding.block_row_slice(h, rank, world)
-    part = flic_b200.workloads.gradient_noise_rows(w, h, c, seed, y0, y1)
-    px = torch.from_numpy(part[None]).cuda()
-    raw_total = w * h * c
-    cap = flic_b200.max_stream_bytes(w, y1 - y0, c)
-    streams = torch.empty(cap, dtype=torch.uint8, device="cuda")
-    off = torch.zeros(2, dtype=torch.int64, device="cuda")
-    out = torch.empty_like(px)
-    counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+    sc = flic_b200.sharding.ShardedImageCodec(codec, w, h, c, args.flags, D.dist, D.rank, D.world)
+    rows = synth_rows_cuda(torch, w, h, c, seed, sc.y0, sc.y1)[None]
     st = torch.cuda.current_stream().cuda_stream
-
-    def step():
-        codec.encode_batch_device(px, streams, off, args.flags, st)
-        if world > 1:
-            dist.all_gather_into_tensor(counts, off[1:2])  # the tiny all-gather of per-GPU byte counts
-        else:
-            counts.copy_(off[1:2])
-        codec.decode_batch_device(streams, off, out, args.flags, st)
-
-    for _ in range(args.warmup):
-        step()
+    full = None
+    for _ in range(W):
+        full = sc.encode(rows, st)
+        got = sc.decode(full, st)
     codec.check(st)
-    assert torch.equal(out, px)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ok = bool(torch.equal(got, rows))
+    comp = int(full.numel()) if D.rank == 0 else 0
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(K)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if rows.numel() < (512 << 20) else None
     launches0 = codec.launches
-    a.record()
-    for _ in range(args.steps):
-        step()
-    b.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t) / args.steps
+    D.barrier()
+    for a, m, b in ev:
+        if flush is not None:
+            flush.fill_(1)  # a rank's share of the image fits in L2 at 8 GPUs: flush between steps
+        a.record()
+        full = sc.encode(rows, st)
+        m.record()
+        sc.decode(full, st)
+        b.record()
+    D.barrier()
     launches = codec.launches - launches0
+    codec.check(st)
+    enc = sum(a.elapsed_time(m) for a, m, _ in ev) / K
+    dec = sum(m.elapsed_time(b) for _, m, b in ev) / K
+    tot, enc, dec = D.max([enc + dec, enc, dec])
+    allok = D.sum([0.0 if ok else 1.0])[0] == 0.0
+    comp = int(D.sum([float(comp)])[0])
+    raw = w * h * c
+    l2 = "l2_flushed_between_steps" if flush is not None else "inputs_exceed_l2"
+    del sc, rows, flush
+    torch.cuda.empty_cache()
+    return {"l2": l2, "value_GBps": round(raw / (tot * 1e-3) / 1e9, 2), "encode_GBps": round(raw / (enc * 1e-3) / 1e9, 2),
+            "decode_GBps": round(raw / (dec * 1e-3) / 1e9, 2), "ms_per_step": round(tot, 4), "steps": K, "scaling": "strong",
+            "width": w, "height": h, "raw_bytes": raw, "compressed_ratio": round(comp / raw, 4),
+            "split": ("block rows over %d ranks; timed: encode + all-gather of (n_blocks, payload_words) + NCCL send/recv of "
+                      "parts into the spliced stream + splice kernel, then cut + send/recv + finish + decode" % D.world)
+                     if D.world > 1 else "none (one GPU)",
+            "round_trip_verified_on_every_rank": bool(allok), "gpu_launches_this_rank": launches, "data": "synthetic (GPU generator)"}
 
-    # ---- untimed: gather, splice, decode the whole image on rank 0
-    n_bytes = int(off[1])
-    sizes = [int(x) for x in counts.tolist()]
-    verified = None
-    if world > 1:
-        pad = max(sizes)
-        buf = torch.zeros(pad, dtype=torch.uint8, device="cuda")
-        buf[:n_bytes] = streams[:n_bytes]
-        got = [torch.zeros(pad, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, got, dst=0)
-        rows = [flic_b200.sharding.block_row_slice(h, r, world) for r in range(world)]
-        maxrows = max(b_ - a_ for a_, b_ in rows)
-        pbuf = torch.zeros((maxrows, w, c), dtype=torch.uint8, device="cuda")
-        pbuf[: y1 - y0] = px[0]
-        pgot = [torch.zeros_like(pbuf) for _ in range(world)] if rank == 0 else None
-        dist.gather(pbuf, pgot, dst=0)
-        if rank == 0:
-            parts = [got[r][: sizes[r]].cpu().numpy() for r in range(world) if sizes[r]]
-            full = flic_b200.splice_block_rows(parts)
-            info = flic_b200.peek(full)
-            d_full = torch.from_numpy(full).cuda()
-            d_off = torch.tensor([0, full.size], dtype=torch.int64, device="cuda")
-            d_out = torch.empty((1, h, w, c), dtype=torch.uint8, device="cuda")
-            codec.decode_batch_device(d_full, d_off, d_out, args.flags, st)
-            codec.check(st)
-            ref = torch.cat([pgot[r][: rows[r][1] - rows[r][0]] for r in range(world)])[None]
-            verified = bool(info["height"] == h and torch.equal(d_out, ref))
-    if rank == 0:
-        total_comp = sum(sizes)
-        print(json.dumps({
-            "metric": METRIC, "value": round(raw_total / (ms * 1e-3) / 1e9, 2), "unit": "GB/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C4", "width": w, "height": h, "channels": c, "raw_bytes": raw_total,
-                       "split": "block rows, one all-gather of int64 byte counts per step (NCCL)" if world > 1 else "none",
-                       "l2": "inputs_exceed_l2", "format": "FLP0 (provisional; NOT the reference bitstream)"},
-            "compressed_ratio": round(total_comp / raw_total, 4), "per_rank_stream_bytes": sizes,
-            "spliced_stream_decodes_to_input": verified, "gpu_launches": launches,
-            "parity": "engine vs FLP0 CPU model only; vs reference: unpinned — licensing gate"}))
-    if world > 1:
-        dist.destroy_process_group()
+
+def e2e_pipelined(D, codec, host_px, cap, n, flags, steps):
+    """End to end through the host-buffer ABI on pinned buffers, software-pipelined across steps: while step k's
+    streams are being decoded (H2D of streams, D2H of pixels), step k+1 is being encoded (H2D of pixels, D2H of
+    streams).  Two stream buffers alternate.  Every step copies its pixels from host memory and reads its decoded
+    pixels back into host memory; the timed region covers `steps` full encode+decode round trips."""
+    import numpy as np
+    import flic_b200
+    torch = D.torch
+    h_in = host_px.numpy()
+    h_str = [torch.empty(cap, dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+    h_off = [np.zeros(n + 1, dtype=np.uint64) for _ in range(2)]
+    h_out = torch.empty_like(host_px).pin_memory().numpy()
+
+    def run(k):
+        # prologue: encode step 0; steady state: encode(i+1) || decode(i); epilogue: decode the last
+        codec.encode_submit(h_in, flags, out=h_str[0], offsets=h_off[0]); codec.wait(flic_b200.OP_ENCODE)
+        nbytes = 0
+        for i in range(k):
+            cur, nxt = i & 1, (i + 1) & 1
+            if i + 1 < k:
+                codec.encode_submit(h_in, flags, out=h_str[nxt], offsets=h_off[nxt])
+            nbytes = int(h_off[cur][n])
+            codec.decode_submit(h_str[cur][:nbytes], h_off[cur], h_out)
+            codec.wait(flic_b200.OP_DECODE)
+            if i + 1 < k:
+                codec.wait(flic_b200.OP_ENCODE)
+        return nbytes
+
+    run(2)
+    assert np.array_equal(h_out, h_in), "host round trip is not lossless"
+    k = max(3, min(steps, 6))
+    D.barrier()
+    t0 = time.perf_counter()
+    nbytes = run(k)
+    D.torch.cuda.synchronize()
+    dt = D.max([time.perf_counter() - t0])[0]
+    raw = h_in.nbytes
+    per_dir = (raw + nbytes) * k / dt / 1e9
+    return {"value": D.world * raw * k / dt / 1e9, "unit": "GB/s", "steps": k,
+            "h2d_bytes_per_step": int(raw + nbytes + 8 * (n + 1)), "d2h_bytes_per_step": int(nbytes + raw + 8 * (n + 1) + 8),
+            "pcie_GBps_per_direction_per_gpu": round(per_dir, 2),
+            "note": "flic_encode_submit + flic_decode_submit + flic_wait on pinned host buffers, encode of step k+1 overlapping "
+                    "decode of step k; host wall clock, max over ranks"}
 
 
 def run_reference(args):
-    """`--impl reference`: the CPU arm.  The reference's own Rust implementation cannot be used (licensing
-    gate, and no Rust toolchain in the image), so this times the only CPU implementation of this path
-    that exists here — the scalar C model of the provisional FLP0 format (oracle/, kind "port") — on all
-    host cores, on a bounded sample of the same workload, and says so in the line."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """`--impl reference`: the reference's own CPU implementation is behind the licensing gate and there is no Rust
+    toolchain here, so this arm is unavailable.  What CAN be timed on the host — the scalar C model of the provisional
+    FLP0 format — is reported under `cpu_model`, explicitly not as the reference."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import flic_b200
-    cfg, n = WORKLOADS[args.workload]
-    batch = flic_b200.workloads.make_batch(cfg, n=min(n, 8))
-    _, h, w, c = batch.shape
-    per_step = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))  # whole run ends within minutes
-    vals, t0 = [], None
-    for i in range(args.warmup + args.steps):
-        if i == args.warmup:
-            t0 = time.perf_counter()
-        r = cpu_model_roundtrip(batch, seconds=per_step)
-        if i >= args.warmup:
-            vals.append(r)
-    step_ms = 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
-    value = statistics.mean(v["value"] for v in vals)
-    cb = dict(vals[-1]); cb["value"] = value; cb["kind"] = "port"
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "width": w, "height": h, "channels": c,
-                   "format": "FLP0 (provisional; NOT the reference bitstream — licensing gate)"},
-        "cpu_baseline": cb, "gpu_launches": 0,
-        "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": GATE}))
+    line = {"impl": "reference", "unavailable": GATE, "metric": METRIC, "value": None, "unit": "GB/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "config": {"workload": args.workload}}
+    if not args.no_cpu:
+        import flic_b200
+        cfg, n = WORKLOADS[args.workload]
+        batch = flic_b200.workloads.make_batch(cfg, n=min(n, DISTINCT))
+        line["cpu_model"] = cpu_model_roundtrip(batch, seconds=15.0)
+    print(json.dumps(line))
 
 
 def main():
@@ -265,180 +431,127 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2x64", choices=sorted(WORKLOADS))
     ap.add_argument("--flags", type=lambda s: int(s, 0), default=0x01)
-    ap.add_argument("--encoder", default="fused", choices=["fused", "staged"])
+    ap.add_argument("--encoder", default="auto", choices=["auto", "fused", "staged"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--c4-height", type=int, default=0, help="override C4's 16384 rows (smoke runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload == "C4":
-        return run_c4_split(args)
 
     import numpy as np
     import torch
-    import torch.distributed as dist
     import flic_b200
 
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D = Dist()
+    numa, all_cpus = bind_to_gpu_numa(D.local)
     flic_b200.build_library()
-    codec = flic_b200.Codec(local)
+    codec = flic_b200.Codec(D.local)
     codec.set_encoder(args.encoder)
+
+    if args.workload == "C4":
+        sampler = ClockSampler(D.local) if D.rank == 0 else None
+        res = c4_split(D, codec, args, args.steps, args.warmup)
+        clocks = sampler.stop() if sampler else None
+        if D.rank == 0:
+            print(json.dumps({"metric": METRIC, "value": res["value_GBps"], "unit": "GB/s", "n_gpus": D.world,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                              "config": {"workload": "C4", "format": FORMAT, "l2": "inputs_exceed_l2"}, "c4": res,
+                              "gpu_launches": res["gpu_launches_this_rank"], "clocks": clocks,
+                              "parity": "engine vs FLP0 CPU model only; vs reference: unpinned — licensing gate"}))
+        D.close()
+        return
 
     cfg, n = WORKLOADS[args.workload]
     # weak scaling: every rank owns its own `n` images (independent units, no data-path collective)
-    batch = flic_b200.workloads.make_batch(cfg, n=n)
+    batch = flic_b200.workloads.make_batch(cfg, n=n, distinct=DISTINCT)
     _, h, w, c = batch.shape
     raw = batch.nbytes
     host_px = torch.from_numpy(batch).pin_memory()
     px = host_px.cuda(non_blocking=True)
-    cap = n * flic_b200.max_stream_bytes(w, h, c)
-    streams = torch.empty(cap, dtype=torch.uint8, device="cuda")
-    off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
-    out = torch.empty_like(px)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if raw < (512 << 20) else None
-    st = torch.cuda.current_stream().cuda_stream
 
-    def step():
-        codec.encode_batch_device(px, streams, off, args.flags, st)
-        codec.decode_batch_device(streams, off, out, args.flags, st)
+    sampler = ClockSampler(D.local) if D.rank == 0 else None
+    main_res = device_roundtrip(D, codec, px, args.flags, args.steps, args.warmup, kernel_times=True)
+    comp, r = main_res["comp"], main_res["comp"] / raw
+    ms_per_step = main_res["ms"]
+    value = D.world * raw / (ms_per_step * 1e-3) / 1e9
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(args.warmup):
-        step()
-    codec.check(st)
-    assert torch.equal(out, px), "round trip is not lossless"
-    comp = int(off[-1].item())
-    r = comp / raw
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing: K steps, per-step events (L2 flush between steps is outside them) ----
-    codec.kernel_times()
-    codec.set_kernel_timing(True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = codec.launches
-    barrier()
-    for a, m, b in ev:
-        if flush is not None:
-            flush.fill_(1)
-        a.record()
-        codec.encode_batch_device(px, streams, off, args.flags, st)
-        m.record()
-        codec.decode_batch_device(streams, off, out, args.flags, st)
-        b.record()
-    barrier()
-    launches = codec.launches - launches0
-    codec.set_kernel_timing(False)
-    ktimes = codec.kernel_times()
-    codec.check(st)
-    enc_ms = sum(a.elapsed_time(m) for a, m, _ in ev)
-    dec_ms = sum(m.elapsed_time(b) for _, m, b in ev)
-    tot = torch.tensor([enc_ms + dec_ms, enc_ms, dec_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    tot_ms, enc_ms, dec_ms = (float(x) for x in tot.tolist())
-    ms_per_step = tot_ms / args.steps
-    value = world * raw / (ms_per_step * 1e-3) / 1e9
-
-    # ---- end to end through the host-buffer ABI: pinned host pixels in, host pixels out ----
     e2e = None
     if not args.no_e2e:
-        h_streams = torch.empty(cap, dtype=torch.uint8).pin_memory().numpy()
-        h_off = np.zeros(n + 1, dtype=np.uint64)
-        h_out = torch.empty_like(host_px).pin_memory().numpy()
-        h_in = host_px.numpy()
-
-        def e2e_step():
-            s, o = codec.encode_batch(h_in, args.flags, out=h_streams, offsets=h_off)
-            codec.decode_batch(s, o, out=h_out)
-            return s.size
-
-        for _ in range(2):
-            e2e_step()
-        assert np.array_equal(h_out, h_in)
-        k = max(3, min(args.steps, 5))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(k):
-            nbytes = e2e_step()
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * raw * k / float(dt) / 1e9, "unit": "GB/s", "steps": k,
-               "h2d_bytes_per_step": int(raw + nbytes + 8 * (n + 1)), "d2h_bytes_per_step": int(nbytes + raw + 8 * (n + 1) + 8),
-               "note": "flic_encode_batch + flic_decode_batch on pinned host buffers; host wall clock, max over ranks"}
-
-    clocks = sampler.stop() if sampler else None  # sampled across warm-up, the device-timed steps and the e2e steps
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        cap = n * flic_b200.max_stream_bytes(w, h, c)
+        e2e = e2e_pipelined(D, codec, host_px, cap, n, args.flags, args.steps)
+    del px
+    torch.cuda.empty_cache()
+    hbm, peak_src = peaks()
+    secondary = None
+    if not args.no_secondary and args.workload == "C2x64":
+        secondary = secondary_lines(D, codec, args, hbm)
+    clocks = sampler.stop() if sampler else None  # sampled across warm-up, the device-timed steps, e2e and secondary
+    if D.rank != 0:
+        D.close()
         return
 
-    hbm, peak_src = peaks()
+    ktimes = main_res["kernels"]
     alg = {"k_histograms": raw, "k_tables": 0, "k_slots": 0, "k_pack": raw + comp, "k_finalize": 0, "k_decode": raw + comp,
            "k_encode": raw + comp, "k_decode_one": raw + comp}
     kernels = {}
+    step_ms_total = ms_per_step * args.steps
     for k, (ms, cnt) in ktimes.items():
         if cnt:
             avg = ms / cnt
-            kernels[k] = {"avg_ms": round(avg, 4), "launches": cnt, "share_of_step": round(ms / tot_ms, 4),
-                          "alg_GBps": round(alg[k] / (avg * 1e-3) / 1e9, 1) if alg[k] else None}
-    dom = max(kernels, key=lambda k: kernels[k]["avg_ms"]) if kernels else None
-    # DRAM bytes per launch from the committed ncu capture of this same workload (profiles/), if there is one
+            kernels[k] = {"avg_ms": round(avg, 4), "launches": cnt, "share_of_step": round(ms / step_ms_total, 4),
+                          "alg_GBps": round(alg[k] / (avg * 1e-3) / 1e9, 1) if alg[k] else None,
+                          "frac_of_hbm_peak": round(alg[k] / (avg * 1e-3) / 1e9 / hbm, 4) if alg[k] else None}
+    enc_frac = (raw + comp) / (main_res["enc_ms"] * 1e-3) / 1e9 / hbm
+    dec_frac = (raw + comp) / (main_res["dec_ms"] * 1e-3) / 1e9 / hbm
+    # the dominant kernel: the longest kernel of the slower path
+    enc_k = [k for k in kernels if k in ("k_encode", "k_histograms", "k_tables", "k_pack", "k_slots", "k_finalize")]
+    dec_k = [k for k in kernels if k in ("k_decode", "k_decode_one")]
+    slow = enc_k if enc_frac <= dec_frac else dec_k
+    dom = max(slow, key=lambda k: kernels[k]["avg_ms"]) if slow else None
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01s2_traffic_c2x64.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic_c2x64.json")) as f:
             tj = json.load(f)
-        if tj.get("workload") == args.workload and dom in tj["kernels"]:
-            traffic, traffic_src = tj["kernels"][dom]["traffic_bytes"], "profiles/r01s2_traffic_c2x64.json (ncu dram__bytes_read+write per launch)"
+        if tj.get("workload") == args.workload:
             for k in kernels:
                 if k in tj["kernels"]:
                     kernels[k]["dram_traffic_bytes"] = tj["kernels"][k]["traffic_bytes"]
+            if dom in tj["kernels"]:
+                traffic, traffic_src = tj["kernels"][dom]["traffic_bytes"], "profiles/r02_traffic_c2x64.json (ncu dram__bytes_read+write per launch)"
     except Exception:
         pass
-    roof = None
-    if dom:
-        ach = alg[dom] / (kernels[dom]["avg_ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-                "frac": round(ach / hbm, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "note": {"k_pack": "k_pack: ALU pipe 68 %, LSU data pipe 67 %, issue 77 % — integer-pipe bound, not HBM bound",
-                         "k_decode": "k_decode: LSU data pipe 76 % busy (LUT reads with 3.4-way bank conflicts), issue 65 % — not HBM bound",
-                         "k_histograms": "k_histograms: ~70 % of measured HBM peak with the residual plane (2N bytes of traffic)"}.get(dom, "")
-                        + " (profiles/r01s2_ncu_full_c2x8.txt)",
-                "algorithmic_bytes_per_launch": alg[dom],
-                "encode_path_frac": round((raw + comp) / (enc_ms / args.steps * 1e-3) / 1e9 / hbm, 4),
-                "decode_path_frac": round((raw + comp) / (dec_ms / args.steps * 1e-3) / 1e9 / hbm, 4)}
+    path_frac = min(enc_frac, dec_frac)
+    roof = {"bound": "hbm", "kernel": dom, "achieved": round(path_frac * hbm, 1), "peak": hbm, "unit": "GB/s",
+            "frac": round(path_frac, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "definition": "frac = min(encode path, decode path) of (1 + r) * N algorithmic bytes per pass / path time / peak; "
+                          "`kernel` is the longest kernel of the slower path (its own fraction is in kernels[...])",
+            "algorithmic_bytes_per_pass": raw + comp,
+            "encode_path_frac": round(enc_frac, 4), "decode_path_frac": round(dec_frac, 4)}
     line = {
-        "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": D.world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "images_per_gpu": n, "width": w, "height": h, "channels": c,
-                   "raw_bytes_per_gpu_step": raw, "flags": args.flags,
-                   "l2": "inputs_exceed_l2" if flush is None else "l2_flushed_between_steps",
-                   "format": "FLP0 (provisional; NOT the reference bitstream — licensing gate)"},
-        "encode_GBps": round(world * raw / (enc_ms / args.steps * 1e-3) / 1e9, 2),
-        "decode_GBps": round(world * raw / (dec_ms / args.steps * 1e-3) / 1e9, 2),
+        "config": {"workload": args.workload, "images_per_gpu": n, "distinct_images": min(n, DISTINCT), "width": w, "height": h,
+                   "channels": c, "raw_bytes_per_gpu_step": raw, "flags": args.flags, "encoder": args.encoder,
+                   "l2": main_res["l2"], "format": FORMAT, "host_numa": numa},
+        "encode_GBps": round(D.world * raw / (main_res["enc_ms"] * 1e-3) / 1e9, 2),
+        "decode_GBps": round(D.world * raw / (main_res["dec_ms"] * 1e-3) / 1e9, 2),
         "compressed_ratio": round(r, 4), "bits_per_pixel": round(8 * comp / (n * w * h), 3),
         "parity": "byte-exact vs FLP0 CPU model (tests/); vs reference: unpinned — licensing gate",
-        "roofline": roof, "kernels": kernels, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+        "roofline": roof, "kernels": kernels, "gpu_launches": main_res["launches"], "clocks": clocks, "e2e": e2e,
+        "secondary": secondary,
+        "cpu_baseline": {"value": None, "unit": "GB/s", "cores": 0, "kind": "unavailable", "sample": GATE},
     }
-    if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_model_roundtrip(batch, seconds=20.0)
+    if D.world == 1 and not args.no_cpu:
+        if all_cpus:
+            os.sched_setaffinity(0, all_cpus)  # the CPU model may use every core again
+        line["cpu_model"] = cpu_model_roundtrip(batch[:DISTINCT], seconds=20.0)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

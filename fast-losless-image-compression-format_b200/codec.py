@@ -15,7 +15,7 @@ BLOCK_W, BLOCK_H, MAX_CODE_LEN = 128, 32, 10
 PRED_LEFT, FLAG_SUBGREEN = 1, 0x10
 FLAG_ONE_STREAM, FLAG_EXACT = 0x20, 0x40   # optional stream layouts (include/flic_b200.h)
 OP_ENCODE, OP_DECODE = 0, 1
-ENCODER_FUSED, ENCODER_STAGED = 0, 1
+ENCODER_FUSED, ENCODER_STAGED, ENCODER_AUTO = 0, 1, 2
 
 _ERR = {
     -1: "invalid argument", -2: "output buffer too small", -3: "malformed stream", -4: "CUDA error",
@@ -69,6 +69,7 @@ def load_library():
         "flic_set_kernel_timing": (i32, [vp, i32]),
         "flic_get_kernel_times": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
         "flic_set_option": (i32, [vp, i32, i32]),
+        "flic_get_phase_clocks": (i32, [vp, C.POINTER(u64)]),
         "flic_host_register": (i32, [vp, u64]),
         "flic_host_unregister": (i32, [vp]),
         "flic_encode_submit": (i32, [vp, vp, u32, u32, u32, u32, u32, vp, u64, vp]),
@@ -90,7 +91,7 @@ EXPORTED = (
     "flic_create flic_destroy flic_strerror flic_last_error flic_version flic_blocks_per_image "
     "flic_max_stream_bytes flic_encode_batch_device flic_decode_batch_device flic_check flic_encode_batch "
     "flic_decode_batch flic_peek flic_splice_block_rows flic_stage_histograms flic_stage_tables "
-    "flic_launch_count flic_set_kernel_timing flic_get_kernel_times flic_set_option flic_host_register "
+    "flic_launch_count flic_set_kernel_timing flic_get_kernel_times flic_set_option flic_get_phase_clocks flic_host_register "
     "flic_host_unregister flic_encode_submit flic_decode_submit flic_wait flic_splice_block_rows_device "
     "flic_splice_plan flic_splice_finish_device flic_split_finish_device"
 ).split()
@@ -175,8 +176,9 @@ class Codec:
         return int(self.lib.flic_launch_count(self.h))
 
     def set_encoder(self, which):
-        """'fused' (default: one pass over the pixels) or 'staged' (round-1 five-kernel pipeline; same bytes)."""
-        self._chk(self.lib.flic_set_option(self.h, 1, {"fused": ENCODER_FUSED, "staged": ENCODER_STAGED}[which]))
+        """'fused' (one pass over the pixels), 'staged' (five-kernel pipeline) or 'auto' (default: by job size);
+        all give the same bytes."""
+        self._chk(self.lib.flic_set_option(self.h, 1, {"fused": ENCODER_FUSED, "staged": ENCODER_STAGED, "auto": ENCODER_AUTO}[which]))
 
     # ---- submit / wait: one encode and one decode may be in flight together ----
     def encode_submit(self, pixels, flags=PRED_LEFT, out=None, offsets=None):
@@ -288,6 +290,12 @@ class Codec:
         cnt = (C.c_uint64 * len(KERNELS))()
         self._chk(self.lib.flic_get_kernel_times(self.h, ms, cnt))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNELS)}
+
+    def phase_clocks(self):
+        """Per-phase SM-cycle sums of k_encode since the last call (needs FLIC_PHASE_CLOCKS=1 at creation)."""
+        cyc = (C.c_uint64 * 8)()
+        self._chk(self.lib.flic_get_phase_clocks(self.h, cyc))
+        return [int(x) for x in cyc]
 
     # ---- stage-level (parity tests) ----
     def stage_histograms(self, pixels, hist, flags=PRED_LEFT, stream=0, flat=None):

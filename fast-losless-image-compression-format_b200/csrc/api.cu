@@ -41,7 +41,7 @@ struct flic_ctx {
     int device = 0;
     char msg[256] = {0};
     std::atomic<uint64_t> launches{0};  // encode and decode workers (flic_*_submit) may both be launching
-    int encoder = FLIC_ENCODER_FUSED;
+    int encoder = FLIC_ENCODER_AUTO;
     // per-block workspace (grown on demand)
     uint64_t ws_blocks = 0;
     bool ws_staged = false;       // the staged encoder's extra arrays are allocated
@@ -54,6 +54,7 @@ struct flic_ctx {
     unsigned long long *d_ticket = nullptr; // fused encoder: block ticket counter (monotonic across launches)
     unsigned long long ticket_base = 0;
     uint32_t fused_epoch = 0;
+    unsigned long long *d_phase = nullptr;  // debug: per-phase cycle sums of k_encode (FLIC_PHASE_CLOCKS=1), else null
     unsigned long long *d_slot_status = nullptr;  // staged encoder, k_slots: 128 epoch-tagged run sums
     uint32_t slot_epoch = 0;
     int slots_max_grid = 0;       // co-resident k_slots CTAs on this device (occupancy API)
@@ -81,12 +82,13 @@ struct KernelTimer {
     flic_ctx *ctx; cudaStream_t s; flic_ctx::Span sp; bool on;
     KernelTimer(flic_ctx *c, int kernel, cudaStream_t st) : ctx(c), s(st), on(c->timing) {
         if (!on) return;
-        std::unique_lock<std::mutex> lk(ctx->span_mu);
-        const bool reuse = !ctx->free_spans.empty();
-        if (reuse) { sp = ctx->free_spans.back(); ctx->free_spans.pop_back(); }
-        lk.unlock();
-        if (reuse) {}
-        else if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) { on = false; return; }
+        bool reuse;
+        {
+            std::lock_guard<std::mutex> lk(ctx->span_mu);
+            reuse = !ctx->free_spans.empty();
+            if (reuse) { sp = ctx->free_spans.back(); ctx->free_spans.pop_back(); }
+        }
+        if (!reuse && (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess)) { on = false; return; }
         sp.kernel = kernel;
         cudaEventRecord(sp.a, s);
     }
@@ -181,7 +183,8 @@ extern "C" int flic_create(int device, flic_ctx **out) {
     flic_ctx *ctx = new (std::nothrow) flic_ctx;
     if (!ctx) return FLIC_E_ARG;
     ctx->device = device;
-    if (const char *e = getenv("FLIC_ENCODER")) ctx->encoder = strcmp(e, "staged") == 0 ? FLIC_ENCODER_STAGED : FLIC_ENCODER_FUSED;
+    if (const char *e = getenv("FLIC_ENCODER"))
+        ctx->encoder = strcmp(e, "staged") == 0 ? FLIC_ENCODER_STAGED : (strcmp(e, "fused") == 0 ? FLIC_ENCODER_FUSED : FLIC_ENCODER_AUTO);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_err, 2 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_err, 0, 2 * sizeof(uint32_t));
@@ -190,6 +193,10 @@ extern "C" int flic_create(int device, flic_ctx **out) {
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ticket, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_ticket, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_err, 4 * sizeof(uint32_t));
+    if (e == cudaSuccess && getenv("FLIC_PHASE_CLOCKS")) {
+        e = cudaMalloc(&ctx->d_phase, FLIC_PHASES * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(ctx->d_phase, 0, FLIC_PHASES * sizeof(unsigned long long));
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_ws, cudaEventDisableTiming);
     if (e == cudaSuccess) e = pipe_create(ctx->enc);
     if (e == cudaSuccess) e = pipe_create(ctx->dec);
@@ -217,7 +224,7 @@ extern "C" void flic_destroy(flic_ctx *ctx) {
     pipe_destroy(ctx->dec);
     cudaDeviceSynchronize();
     free_workspace(ctx);
-    cudaFree(ctx->d_err); cudaFree(ctx->d_slot_status); cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_err); cudaFree(ctx->d_slot_status); cudaFree(ctx->d_ticket); cudaFree(ctx->d_phase);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->ev_ws) cudaEventDestroy(ctx->ev_ws);
     for (auto &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -229,7 +236,7 @@ extern "C" int flic_set_option(flic_ctx *ctx, int option, int value) {
     if (!ctx) return FLIC_E_ARG;
     switch (option) {
         case FLIC_OPT_ENCODER:
-            if (value != FLIC_ENCODER_FUSED && value != FLIC_ENCODER_STAGED) return FLIC_E_ARG;
+            if (value != FLIC_ENCODER_FUSED && value != FLIC_ENCODER_STAGED && value != FLIC_ENCODER_AUTO) return FLIC_E_ARG;
             ctx->encoder = value;
             return FLIC_OK;
         default: return FLIC_E_ARG;
@@ -290,7 +297,7 @@ extern "C" int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t
     if (!ctx || !d_hist || !d_table || n_blocks_total == 0 || n_blocks_total >= (1ull << 31)) return FLIC_E_ARG;
     CU(cudaSetDevice(ctx->device));
     { KernelTimer t(ctx, FLIC_K_TABLES, (cudaStream_t)stream);
-      if (ctx->encoder == FLIC_ENCODER_FUSED) launch_tables_cta(d_hist, n_blocks_total, d_table, d_bits, (cudaStream_t)stream);  // the fused kernel's builder
+      if (ctx->encoder != FLIC_ENCODER_STAGED) launch_tables_cta(d_hist, n_blocks_total, d_table, d_bits, (cudaStream_t)stream);  // the fused kernel's builder
       else launch_tables(d_hist, n_blocks_total, d_table, d_bits, (cudaStream_t)stream); }
     ctx->launches += 1;
     CU(cudaGetLastError());
@@ -305,7 +312,11 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
     int rc = make_geo(d_pixels, n, w, h, c, flags, &g);
     if (rc) return rc;
     if (capacity_bytes < 4ull * n * (kHdrWords + (uint64_t)g.nb + 1)) return FLIC_E_CAPACITY;
-    const bool staged = ctx->encoder == FLIC_ENCODER_STAGED && !(flags & (FLIC_FLAG_ONE_STREAM | FLIC_FLAG_EXACT));
+    // AUTO: below kAutoBlocks the job is a latency chain (launches, one wave of CTAs) and the two-launch fused path
+    // wins; above it the staged pipeline's higher issue efficiency does (measured: DESIGN.md §5)
+    constexpr uint64_t kAutoBlocks = 4096;
+    const bool want_staged = ctx->encoder == FLIC_ENCODER_STAGED || (ctx->encoder == FLIC_ENCODER_AUTO && (uint64_t)n * g.nb >= kAutoBlocks);
+    const bool staged = want_staged && !(flags & (FLIC_FLAG_ONE_STREAM | FLIC_FLAG_EXACT));
     CU(cudaSetDevice(ctx->device));
     rc = ensure_workspace(ctx, (uint64_t)n * g.nb, staged);
     if (rc) return rc;
@@ -321,7 +332,7 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
         unsigned grid;
         { KernelTimer t(ctx, FLIC_K_ENCODE, s);
           grid = launch_encode_fused(d_pixels, g, (uint32_t *)d_streams, cap_words, ctx->d_dirE, ctx->d_status, ctx->d_ticket,
-                                     ctx->ticket_base, ctx->fused_epoch, ctx->d_err, s); }
+                                     ctx->ticket_base, ctx->fused_epoch, ctx->d_err, ctx->d_phase, s); }
         ctx->ticket_base += (uint64_t)n * g.nb + grid;  // every CTA's last claim fails
         { KernelTimer t(ctx, FLIC_K_FINALIZE, s);
           launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s); }
@@ -435,6 +446,16 @@ static int check_word(flic_ctx *ctx, int word, cudaStream_t s) {
     return report_device_errors(ctx, ctx->h_err[word]);
 }
 
+extern "C" int flic_get_phase_clocks(flic_ctx *ctx, uint64_t cycles[FLIC_PHASES]) {
+    if (!ctx || !cycles) return FLIC_E_ARG;
+    if (!ctx->d_phase) return FLIC_E_UNSUPPORTED;  // the context was created without FLIC_PHASE_CLOCKS=1
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(cycles, ctx->d_phase, FLIC_PHASES * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemset(ctx->d_phase, 0, FLIC_PHASES * sizeof(unsigned long long)));
+    return FLIC_OK;
+}
+
 extern "C" int flic_check(flic_ctx *ctx, void *stream) {
     if (!ctx) return FLIC_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
@@ -460,23 +481,43 @@ extern "C" int flic_host_unregister(void *p) {
 }
 
 namespace {
-// Pins a caller buffer for the duration of one host-API call when it is pageable: cudaMemcpyAsync on pageable
-// memory is staged through the driver's bounce buffer and serialises with the host, which turns the three-stream
-// pipeline into a sequence.  Buffers that are already pinned (cudaHostAlloc / flic_host_register — what a caller
-// on the fast path should do once, up front) are left alone; a failed registration just means the slow copies.
+// Pins the caller's two buffers for the duration of one host-API call when they are pageable: cudaMemcpyAsync on
+// pageable memory is staged through the driver's bounce buffer and serialises with the host, which turns the
+// three-stream pipeline into a sequence.  Buffers that are already pinned (cudaHostAlloc / flic_host_register —
+// what a caller on the fast path should do once, up front) are left alone; a failed registration just means the
+// slow copies.  Registration is by whole pages: when the two buffers share a page (neighbours on the heap) they
+// are registered as ONE range — two overlapping registrations would leave one buffer half pinned, and a copy
+// that straddles pinned and pageable memory is an error.
 struct AutoPin {
-    void *base = nullptr;
-    AutoPin(const void *p, uint64_t bytes) {
-        static const bool off = getenv("FLIC_NO_AUTOPIN") != nullptr;
-        if (off || !p || bytes < (1u << 20)) return;  // small buffers: registration costs more than it saves
+    void *base[2] = {nullptr, nullptr};
+    static bool pageable(const void *p) {
         cudaPointerAttributes a;
-        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return; }
-        if (a.type != cudaMemoryTypeUnregistered) return;
-        const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)4095, hi = ((uintptr_t)p + bytes + 4095) & ~(uintptr_t)4095;
-        if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterPortable) == cudaSuccess) base = (void *)lo;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeUnregistered;
+    }
+    void pin(int slot, uintptr_t lo, uintptr_t hi) {
+        if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterPortable) == cudaSuccess) base[slot] = (void *)lo;
         else cudaGetLastError();
     }
-    ~AutoPin() { if (base) cudaHostUnregister(base); }
+    AutoPin(const void *p0, uint64_t n0, const void *p1, uint64_t n1) {
+        static const bool off = getenv("FLIC_NO_AUTOPIN") != nullptr;
+        if (off) return;
+        const uintptr_t pg = 4095;
+        uintptr_t lo[2] = {(uintptr_t)p0 & ~pg, (uintptr_t)p1 & ~pg};
+        uintptr_t hi[2] = {((uintptr_t)p0 + n0 + pg) & ~pg, ((uintptr_t)p1 + n1 + pg) & ~pg};
+        // small buffers: registration costs more than it saves
+        bool want[2] = {p0 && n0 >= (1u << 20) && pageable(p0), p1 && n1 >= (1u << 20) && pageable(p1)};
+        if (want[0] && want[1] && lo[0] < hi[1] && lo[1] < hi[0]) {  // the page ranges overlap: one registration
+            pin(0, lo[0] < lo[1] ? lo[0] : lo[1], hi[0] > hi[1] ? hi[0] : hi[1]);
+            return;
+        }
+        for (int i = 0; i < 2; ++i)
+            if (want[i]) pin(i, lo[i], hi[i]);
+    }
+    ~AutoPin() {
+        for (int i = 0; i < 2; ++i)
+            if (base[i]) cudaHostUnregister(base[i]);
+    }
 };
 }  // namespace
 
@@ -534,7 +575,7 @@ static int encode_batch_impl(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n,
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_staging(ctx, P, m * img_bytes, m * img_worst, (uint64_t)m + 1);
     if (rc) return rc;
-    AutoPin pin_in(h_pixels, (uint64_t)n * img_bytes), pin_out(h_streams, capacity_bytes);
+    AutoPin pin(h_pixels, (uint64_t)n * img_bytes, h_streams, capacity_bytes);
     const uint32_t chunks = (n + m - 1) / m;
     uint64_t out_pos = 0;
     h_offsets[0] = 0;
@@ -677,7 +718,7 @@ static int decode_batch_impl(flic_ctx *ctx, const uint8_t *h_streams, const uint
     }
     if (need > pixels_capacity) return FLIC_E_CAPACITY;
     CU(cudaSetDevice(ctx->device));
-    AutoPin pin_in(h_streams + h_offsets[0], h_offsets[n] - h_offsets[0]), pin_out(h_pixels, need);
+    AutoPin pin(h_streams + h_offsets[0], h_offsets[n] - h_offsets[0], h_pixels, need);
     int rc = FLIC_OK;
     uint64_t pix_pos = 0;
     for (uint32_t lo = 0; lo < n && rc == FLIC_OK;) {

@@ -199,7 +199,8 @@ void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d
 // fused single-pass encoder; returns the grid size (every CTA draws one ticket beyond the last block)
 unsigned launch_encode_fused(const uint8_t *d_pixels, const Geo &g, uint32_t *d_streams, uint64_t capacity_words,
                              unsigned long long *d_dirE, unsigned long long *d_status, unsigned long long *d_ticket,
-                             unsigned long long ticket_base, uint32_t epoch, uint32_t *d_err, cudaStream_t s);
+                             unsigned long long ticket_base, uint32_t epoch, uint32_t *d_err, unsigned long long *d_phase_clk,
+                             cudaStream_t s);
 // tensor_map: a 128-byte CUtensorMap over the pixel buffer (api.cu: make_pixel_map), or nullptr
 void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offsets, const Geo &g,
                    uint8_t *d_pixels, uint32_t *d_err, const void *tensor_map, cudaStream_t s);

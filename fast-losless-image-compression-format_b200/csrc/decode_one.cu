@@ -3,20 +3,23 @@
 // the first) starts.  This is the pessimistic case VERDICT r1 item 2 asks to be measured: the only parallelism
 // inside a block is what the decoder can recover by itself.
 //
-// One CTA (256 threads) per block, self-synchronising sub-sequence decode (Weißenberger & Schmidt style):
+// One CTA (256 threads) per block, self-synchronising sub-sequence decode (after Weißenberger & Schmidt):
 //   0. the block's stream is copied to shared memory once, coalesced (the only HBM read); warp 0 builds
 //      the 2^kL-entry LUT meanwhile;
-//   1. the stream is cut into 256 sub-sequences of SW words; every thread decodes its own from its first
-//      bit — a guess, wrong more often than not — and records where symbols start in a bit mask;
-//   2. thread t restarts from the position where thread t-1's chain really ended and runs until it lands on
-//      a bit its guessed chain had marked (Huffman decoding is deterministic: from there on the two chains
-//      are one); typically a handful of symbols.  Chains that do not meet inside the sub-sequence push the
-//      correction on to the next thread, round by round, until nothing moves;
-//   3. symbol counts are popcounts of the masks; a block-wide scan gives every thread its first symbol index;
-//   4. every thread decodes its symbols again from its true start into a residual tile (32 rows x row bytes);
+//   1. the stream is cut into 256 sub-sequences of SW words.  Thread t starts decoding kOverlapBits BEFORE its
+//      sub-sequence — from a bit that is a symbol boundary only by luck — and relies on Huffman codes
+//      re-synchronising within a few symbols: it records the first boundary b it reaches inside its
+//      sub-sequence, counts the symbols from there to the first boundary e past its end;
+//   2. the chain is consistent when every thread's b equals its predecessor's e.  A thread whose b is wrong
+//      decodes again from the predecessor's e; if that moves its own e, the next thread follows in the next
+//      round, until nothing moves (fixed-length-like codes, which never re-synchronise, need one round per
+//      sub-sequence: that is the price of this layout);
+//   3. a block-wide scan of the symbol counts gives every thread its first symbol index;
+//   4. every thread decodes its symbols once more from its true start into a DENSE residual buffer (symbol i
+//      at byte i: no per-symbol pixel bookkeeping);
 //   5. un-prediction as scans: column 0 is a byte-wise prefix down the rows (one warp), a row is a byte-wise
-//      prefix along the row (lane-local over four pixels, then a warp scan); rows leave as fully coalesced
-//      128-bit stores.
+//      prefix along the row (lane-local over four pixels, then a warp scan); the coded bytes are spread to
+//      their channels with one PRMT per pixel; rows leave as fully coalesced 128-bit stores.
 // Cost relative to decode.cu's one-lane-per-row reader: every symbol is looked up a little over twice, and
 // the residuals make a round trip through shared memory.
 //
@@ -28,16 +31,13 @@ namespace flic {
 constexpr int kOneThreads = 256;
 constexpr int kOneWarps = kOneThreads / 32;
 
+constexpr uint32_t kOverlapBits = 64;  // speculative run-in before a sub-sequence (typical codes re-synchronise in ~10 symbols)
+
 template <int C>
 struct OneSmem {
     static constexpr int kMaxWords = kBH * ((kBW * C * kL + 31) / 32);  // longest legal block stream
-    static constexpr int kMaskWords = ((kMaxWords + kOneThreads - 1) / kOneThreads) * kOneThreads;
-    static constexpr int kTP = kBW * C + 16;  // residual tile row pitch in bytes
     uint32_t sst[kMaxWords + 4];              // the block's stream, then zero words
-    union {
-        uint32_t mask[kMaskWords];            // steps 1-3: bit b of thread t's words = a symbol starts at bit t*S + b
-        uint8_t tile[kBH * kTP];              // steps 4-5: residual bytes, row-major
-    } u;
+    uint8_t res[kBH * kBW * C + 64];          // residual bytes in symbol order (flat channels have none)
     uint16_t lut[kLutSize];
     LutScratch sc;
     uint32_t E[kOneThreads];                  // where each thread's chain ends = where the next one's starts
@@ -50,27 +50,29 @@ __device__ __forceinline__ uint32_t peek_bits(const uint32_t *sst, uint32_t pos)
     const uint32_t wi = pos >> 5;
     return __funnelshift_l(sst[wi + 1], sst[wi], pos);  // the 32 bits from `pos` on, MSB-first
 }
+// length of the code that starts at bit `pos` / the whole LUT entry (len | symbol << 8)
+__device__ __forceinline__ uint32_t lut_at(const char *lutb, const uint32_t *sst, uint32_t pos) {
+    return *reinterpret_cast<const uint16_t *>(lutb + ((peek_bits(sst, pos) >> (31 - kL)) & (2 * kLutSize - 2)));
+}
 
-// four pixels, C valid low bytes each (higher bytes: junk), from the lane's C packed words
-template <int C>
-__device__ __forceinline__ void unpack4(const uint32_t *w, uint32_t (&px)[4]) {
-    if (C == 4) { px[0] = w[0]; px[1] = w[1 % C]; px[2] = w[2 % C]; px[3] = w[3 % C]; }
-    else if (C == 3) {
+// four pixels, CS valid low bytes each (higher bytes: junk), from CS packed words
+__device__ __forceinline__ void unpack4(int CS, const uint32_t *w, uint32_t (&px)[4]) {
+    if (CS == 4) { px[0] = w[0]; px[1] = w[1]; px[2] = w[2]; px[3] = w[3]; }
+    else if (CS == 3) {
         px[0] = w[0];
-        px[1] = __byte_perm(w[0], w[1 % C], 0x4543);
-        px[2] = __byte_perm(w[1 % C], w[2 % C], 0x4432);
-        px[3] = w[2 % C] >> 8;
-    } else if (C == 2) { px[0] = w[0]; px[1] = w[0] >> 16; px[2] = w[1 % C]; px[3] = w[1 % C] >> 16; }
+        px[1] = __byte_perm(w[0], w[1], 0x4543);
+        px[2] = __byte_perm(w[1], w[2], 0x4432);
+        px[3] = w[2] >> 8;
+    } else if (CS == 2) { px[0] = w[0]; px[1] = w[0] >> 16; px[2] = w[1]; px[3] = w[1] >> 16; }
     else { px[0] = w[0]; px[1] = w[0] >> 8; px[2] = w[0] >> 16; px[3] = w[0] >> 24; }
 }
 
 template <int C>
-__global__ void __launch_bounds__(kOneThreads) k_decode_one(const uint32_t *__restrict__ streams,
-                                                           const unsigned long long *__restrict__ offsets, Geo g,
-                                                           uint8_t *__restrict__ pixels, uint32_t *err) {
+__global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *__restrict__ streams,
+                                                              const unsigned long long *__restrict__ offsets, Geo g,
+                                                              uint8_t *__restrict__ pixels, uint32_t *err) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     OneSmem<C> &sm = *reinterpret_cast<OneSmem<C> *>(smem_raw);
-    constexpr int kTP = OneSmem<C>::kTP;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t gb = blockIdx.x;
     const BlockPos p = block_pos(g, gb);
@@ -118,137 +120,93 @@ __global__ void __launch_bounds__(kOneThreads) k_decode_one(const uint32_t *__re
     if (nobits || nsym == 0) {
         // nothing to read: every coded byte is the sole symbol
         const uint32_t fill = (uint32_t)(sm.lut[0] >> 8) * 0x01010101u;
-        uint32_t *t32 = reinterpret_cast<uint32_t *>(sm.u.tile);
-        for (int i = tid; i < kBH * kTP / 4; i += kOneThreads) t32[i] = fill;
+        uint32_t *r32 = reinterpret_cast<uint32_t *>(sm.res);
+        for (int i = tid; i < (int)(sizeof sm.res / 4); i += kOneThreads) r32[i] = fill;
     } else {
-        // ---- 1. speculative chains
+        // an incomplete code (only a damaged table has one) leaves zero-length LUT entries that would stall a chain:
+        // make them consume one bit, so that the loops below need no guard
+        for (int i = tid; i < kLutSize; i += kOneThreads)
+            if ((sm.lut[i] & 0xFFu) == 0) sm.lut[i] |= 1u;
+        __syncthreads();
+
+        // ---- 1. speculative chains with a run-in
         const uint32_t nbits = 32u * nw;
         const uint32_t SW = max(1u, (nw + kOneThreads - 1) / kOneThreads), S = 32u * SW;
         const uint32_t start = (uint32_t)tid * S, limit = min(start + S, nbits);
         const bool active = start < nbits;
-        uint32_t *mymask = sm.u.mask + (uint32_t)tid * SW;
-        uint32_t myend = nbits;
+        uint32_t b = nbits, e = nbits, cnt = 0;  // first boundary in the sub-sequence, first boundary past it, symbols between
         if (active) {
-            uint32_t pos = start, w = 0, cur = 0;
-            while (pos < limit) {
-                const uint32_t rel = pos - start;
-                if ((rel >> 5) != w) {
-                    mymask[w] = cur;
-                    for (++w; w < (rel >> 5); ++w) mymask[w] = 0;
-                    cur = 0;
-                }
-                cur |= 1u << (rel & 31);
-                const uint32_t e = *reinterpret_cast<const uint16_t *>(lutb + ((peek_bits(sm.sst, pos) >> (31 - kL)) & (2 * kLutSize - 2)));
-                pos += max(e & 0xFFu, 1u);
-            }
-            mymask[w] = cur;
-            for (++w; w < SW; ++w) mymask[w] = 0;
-            myend = pos;
-        } else {
-            for (uint32_t w = 0; w < SW; ++w) mymask[w] = 0;
+            uint32_t pos = start > kOverlapBits ? start - kOverlapBits : 0u;
+            while (pos < start) pos += lut_at(lutb, sm.sst, pos) & 0xFFu;
+            b = pos;
+            while (pos < limit) { pos += lut_at(lutb, sm.sst, pos) & 0xFFu; ++cnt; }
+            e = pos;
         }
-        sm.E[tid] = myend;
+        sm.E[tid] = e;
         __syncthreads();
 
-        // ---- 2. synchronisation rounds
-        uint32_t mystart = start;
+        // ---- 2. make the chain consistent: b[t] must be e[t-1]
         for (;;) {
             const uint32_t prev = tid ? sm.E[tid - 1] : 0u;
             bool changed = false;
-            if (active && tid && prev != mystart) {
-                mystart = prev;
-                const uint32_t olde = myend;
-                if (prev >= limit) {  // the predecessor's last symbol runs past this whole sub-sequence
-                    for (uint32_t w = 0; w < SW; ++w) mymask[w] = 0;
-                    myend = prev;
-                } else {
-                    uint32_t pos = prev, w = (pos - start) >> 5;
-                    for (uint32_t i = 0; i < w; ++i) mymask[i] = 0;
-                    uint32_t old = mymask[w], cur = 0;
-                    bool synced = false;
-                    while (pos < limit) {
-                        const uint32_t rel = pos - start;
-                        if ((rel >> 5) != w) {
-                            mymask[w] = cur;
-                            for (++w; w < (rel >> 5); ++w) mymask[w] = 0;
-                            old = mymask[w];
-                            cur = 0;
-                        }
-                        const uint32_t bit = 1u << (rel & 31);
-                        if (old & bit) {  // the guessed chain passed through here: from now on it is the true one
-                            mymask[w] = cur | (old & ~(bit - 1u));
-                            synced = true;
-                            break;
-                        }
-                        cur |= bit;
-                        const uint32_t e = *reinterpret_cast<const uint16_t *>(lutb + ((peek_bits(sm.sst, pos) >> (31 - kL)) & (2 * kLutSize - 2)));
-                        pos += max(e & 0xFFu, 1u);
-                    }
-                    if (!synced) {
-                        mymask[w] = cur;
-                        for (++w; w < SW; ++w) mymask[w] = 0;
-                        myend = pos;
-                    }
-                }
-                changed = myend != olde;
+            if (active && prev != b) {
+                b = prev;
+                uint32_t pos = prev;
+                cnt = 0;
+                while (pos < limit) { pos += lut_at(lutb, sm.sst, pos) & 0xFFu; ++cnt; }
+                changed = pos != e;
+                e = pos;
             }
             __syncthreads();  // everyone has read its predecessor's end
-            sm.E[tid] = myend;
+            sm.E[tid] = e;
             if (!__syncthreads_or(changed)) break;
         }
 
-        // ---- 3. symbol counts -> first symbol index of every thread
-        uint32_t cnt = 0;
-        for (uint32_t w = 0; w < SW; ++w) cnt += __popc(mymask[w]);
+        // ---- 3. first symbol index of every thread
         const uint32_t incl = warp_incl_scan(cnt, lane);
         if (lane == 31) sm.wsum[warp] = incl;
-        const uint32_t tstart = tid ? sm.E[tid - 1] : 0u;
-        __syncthreads();  // all mask reads are done: the tile (same memory) may be written from here on
+        __syncthreads();
         uint32_t base = incl - cnt, total = 0;
 #pragma unroll
         for (int k = 0; k < kOneWarps; ++k) { const uint32_t s = sm.wsum[k]; base += k < warp ? s : 0u; total += s; }
-        if (total < nsym && tid == 0) atomicOr(err, kErrFormat);  // the stream holds fewer symbols than the block has (a few more: its padding)
+        if (total < nsym && tid == 0) atomicOr(err, kErrFormat);  // fewer symbols than the block has (a few more: the padding)
 
-        // ---- 4. the real decode, into the residual tile
+        // ---- 4. the real decode, into the dense residual buffer
         if (cnt && base < nsym) {
             const uint32_t n = min(cnt, nsym - base);
-            const uint32_t pix = base / CS;
-            uint32_t k = base - pix * CS, row = pix / p.bwa, x = pix - row * p.bwa;
-            uint32_t chmap = 0;  // nibble j: the j-th coded channel
-            {
-                int j = 0;
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch)
-                    if (!((fmask >> ch) & 1u)) chmap |= (uint32_t)ch << (4 * j++);
-            }
-            uint8_t *tp = sm.u.tile + row * kTP + x * C;
-            uint32_t pos = tstart;
+            uint8_t *dst = sm.res + base;
+            uint32_t pos = b;
             for (uint32_t i = 0; i < n; ++i) {
-                const uint32_t e = *reinterpret_cast<const uint16_t *>(lutb + ((peek_bits(sm.sst, pos) >> (31 - kL)) & (2 * kLutSize - 2)));
-                pos += max(e & 0xFFu, 1u);
-                tp[(chmap >> (4 * k)) & 15u] = (uint8_t)(e >> 8);
-                if (++k == CS) {
-                    k = 0; tp += C;
-                    if (++x == p.bwa) { x = 0; ++row; tp = sm.u.tile + row * kTP; }
-                }
+                const uint32_t en = lut_at(lutb, sm.sst, pos);
+                pos += en & 0xFFu;
+                dst[i] = (uint8_t)(en >> 8);
             }
         }
     }
     __syncthreads();
 
     // ---- 5. un-prediction and stores
+    // coded byte j of a pixel belongs to the j-th channel that is not flat: one PRMT spreads a pixel's CS bytes
+    // to their channels (selector nibble 4 = a zero byte, for the flat ones)
+    uint32_t sel = 0;
+    {
+        uint32_t j = 0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) sel |= ((ch < C && !((fmask >> ch) & 1u)) ? j++ : 4u) << (4 * ch);
+    }
     const uint32_t fb = ((fmask & 1u) ? 0xFFu : 0u) | ((fmask & 2u) ? 0xFF00u : 0u) | ((fmask & 4u) ? 0xFF0000u : 0u) |
                         ((fmask & 8u) ? 0xFF000000u : 0u);
-    const uint32_t keep = ~fb, fl = fvals & fb;
+    const uint32_t fl = fvals & fb;
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) != 0 && C >= 3;
+    const uint32_t rowsym = p.bwa * CS;            // coded bytes per row
+    const bool word_rows = (rowsym & 3u) == 0;     // every lane's 4*CS bytes start on a word
     if (warp == 0) {  // column 0: pixel (r, 0) = sum of the first residuals of rows 0..r
         uint32_t fp = 0;
         if (lane < (int)p.bha) {
-            const uint8_t *t = sm.u.tile + lane * kTP;
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) fp |= (uint32_t)t[ch] << (8 * ch);
+            const uint8_t *t = sm.res + lane * rowsym;
+            for (uint32_t j = 0; j < CS; ++j) fp |= (uint32_t)t[j] << (8 * j);
         }
-        fp &= keep;
+        fp = __byte_perm(fp, 0u, sel);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, fp, d);
@@ -260,20 +218,21 @@ __global__ void __launch_bounds__(kOneThreads) k_decode_one(const uint32_t *__re
     const int npx = max(0, min(4, (int)p.bwa - 4 * lane));
     for (int r = warp; r < (int)p.bha; r += kOneWarps) {
         const uint32_t above = r ? sm.vrow[r - 1] : 0u;
-        uint32_t w[C], px[4];
-        const uint32_t *t = reinterpret_cast<const uint32_t *>(sm.u.tile + r * kTP + 4 * C * lane);
-        if (C == 4) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(t);
-            w[0] = q.x; w[1 % C] = q.y; w[2 % C] = q.z; w[3 % C] = q.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < C; ++j) w[j] = t[j];
+        uint32_t w[4] = {0, 0, 0, 0}, px[4];
+        const uint8_t *t = sm.res + r * rowsym + 4 * CS * lane;
+        if (npx) {
+            if (word_rows) {
+                const uint32_t *t32 = reinterpret_cast<const uint32_t *>(t);
+                for (uint32_t j = 0; j < CS; ++j) w[j] = t32[j];
+            } else {
+                for (uint32_t j = 0; j < 4 * CS; ++j) w[j >> 2] |= (uint32_t)t[j] << (8 * (j & 3));  // ragged block width
+            }
         }
-        unpack4<C>(w, px);
-        px[0] &= keep;  // flat channels carry no residuals: whatever the tile holds there stays out of the sums
-        px[1] = __vadd4(px[0], px[1] & keep);
-        px[2] = __vadd4(px[1], px[2] & keep);
-        px[3] = __vadd4(px[2], px[3] & keep);
+        unpack4((int)CS, w, px);
+        px[0] = __byte_perm(px[0], 0u, sel);
+        px[1] = __vadd4(px[0], __byte_perm(px[1], 0u, sel));
+        px[2] = __vadd4(px[1], __byte_perm(px[2], 0u, sel));
+        px[3] = __vadd4(px[2], __byte_perm(px[3], 0u, sel));
         // the lane's last real pixel (lanes past the block's right edge add nothing)
         uint32_t run = npx >= 4 ? px[3] : (npx == 3 ? px[2] : (npx == 2 ? px[1] : (npx == 1 ? px[0] : 0u)));
 #pragma unroll
@@ -287,7 +246,7 @@ __global__ void __launch_bounds__(kOneThreads) k_decode_one(const uint32_t *__re
         uint32_t o[C];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            uint32_t v = (__vadd4(px[i], before) & keep) | fl;
+            uint32_t v = (__vadd4(px[i], before) & ~fb) | fl;
             if (sg) v = addgreen4(v);
             px[i] = v;
         }

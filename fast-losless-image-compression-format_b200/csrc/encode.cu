@@ -832,27 +832,27 @@ struct TabScratch {           // aliases the sub-histograms (dead once every thr
 static_assert(sizeof(TabScratch) <= kEncWarps * 256 * 4, "table scratch must fit in the sub-histograms");
 
 // FLP0 §3.3 step 2 for one thread: leaves W[0..n) ascending -> parents P[q] of the internal nodes q < n-2
-// (node k is created in step k; n-2 is the root).  Both queues' first two entries live in registers and the
-// loads that replace them are issued two picks ahead, so the loop-carried chain is compare + select + add.
+// (node k is created in step k; n-2 is the root).  Only the two queue heads live in registers: the kernel is
+// bound by issue slots, not by this loop's latency, so the loop is kept as short as it can be (a version that
+// prefetched two entries per queue ran 40 instructions per step against 20 here).
 // A leaf wins a tie against an internal node (oracle: flp0_build_lengths).
 __device__ __forceinline__ void two_queue_merge(const uint32_t *W, uint32_t *IW, uint16_t *P, int n) {
     int leaf = 0, root = 0;
-    uint32_t lw = W[0], lw1 = W[1], lw2 = n > 2 ? W[2] : kInf;
-    uint32_t iw = kInf, iw1 = kInf;
+    uint32_t lw = W[0], iw = kInf;
     for (int k = 0; k < n - 1; ++k) {
         uint32_t sum = 0;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             if (lw <= iw) {
                 sum += lw; ++leaf;
-                lw = lw1; lw1 = lw2; lw2 = leaf + 2 < n ? W[leaf + 2] : kInf;
+                lw = leaf < n ? W[leaf] : kInf;
             } else {
                 sum += iw; P[root] = (uint16_t)k; ++root;
-                iw = iw1; iw1 = root + 1 < k ? IW[root + 1] : kInf;
+                iw = root < k ? IW[root] : kInf;
             }
         }
         IW[k] = sum;
-        if (root == k) iw = sum; else if (root + 1 == k) iw1 = sum;  // node k joins the internal queue
+        if (root == k) iw = sum;  // node k is the only internal node waiting
     }
 }
 
@@ -1005,8 +1005,16 @@ template <int C, bool SG>
 __global__ void __launch_bounds__(kEncThreads, kFusedCtas)
 k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ streams, uint64_t capacity_words,
          unsigned long long *__restrict__ dirE, unsigned long long *status, unsigned long long *ticket,
-         unsigned long long ticket_base, uint32_t epoch, uint32_t *err, PackMul pm) {
+         unsigned long long ticket_base, uint32_t epoch, uint32_t *err, PackMul pm, unsigned long long *phase_clk) {
     __shared__ __align__(16) FusedSmem sm;
+    // phase_clk (debug, normally null): thread 0 of every CTA adds the cycles it spent per phase
+    long long t_prev = phase_clk ? clock64() : 0;
+#define FLIC_PHASE(i)                                                       \
+    if (phase_clk && tid == 0) {                                            \
+        const long long t_now = clock64();                                  \
+        atomicAdd(phase_clk + (i), (unsigned long long)(t_now - t_prev));   \
+        t_prev = t_now;                                                     \
+    }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t total = (uint64_t)g.n * g.nb;
     const bool one = one_stream(g.flags), exact = (g.flags & FLIC_FLAG_EXACT) != 0;
@@ -1028,6 +1036,11 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
         if (gb >= total) break;
         const BlockPos p = block_pos(g, gb);
         const int nvl = C * max(0, min(4, (int)p.bwa - 4 * lane));  // real bytes of this lane in a real row
+        // "all four pixels are real", from its own comparison: with C == 1 ptxas 12.9 turns `nvl == 4` into the
+        // predicate output of the VIMNMX that computes the min, and on sm_100a that predicate came out inverted
+        // (partial lanes took the full-lane path: caught by the C == 1 ragged-width parity cases)
+        const bool lane_full = 4 * lane + 4 <= (int)p.bwa;
+        FLIC_PHASE(0)  // ticket + zero-fill + barrier
 
         // ---- A. rows -> residuals -> tile + sub-histograms -------------------------------------------
         {
@@ -1074,12 +1087,12 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
                         const uint32_t vm = nb == 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
                         orw[C == 4 ? 0 : j] |= x & vm;
                     }
-                    if (C == 4 && __all_sync(0xFFFFFFFFu, nvl == 4 * C && ((res[0] | res[1 % C] | res[2 % C] | res[3 % C]) & 0xFF000000u) == 0)) {
+                    if (C == 4 && __all_sync(0xFFFFFFFFu, lane_full && ((res[0] | res[1 % C] | res[2 % C] | res[3 % C]) & 0xFF000000u) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 4 * C; ++j)
                             if ((j & 3) != 3) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[j >> 2], j & 3)), 1u);
                         ++zero_rows;  // an all-zero alpha row (opaque plane): counted once, not looked up
-                    } else if (nvl == 4 * C) {
+                    } else if (lane_full) {
 #pragma unroll
                         for (int j = 0; j < 4 * C; ++j) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[j >> 2], j & 3)), 1u);
                     } else if (nvl > 0) {
@@ -1098,6 +1111,7 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
             }
         }
         __syncthreads();
+        FLIC_PHASE(1)  // loads, residuals, sub-histograms
 
         // ---- B. this thread's symbol count; flat channels (FLP0 §2b) ----------------------------------
         uint32_t cnt = 0, flatmask, flatvals;
@@ -1122,6 +1136,7 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
             flatvals = first & (flatb * 0xFFu);
         }
         __syncthreads();  // every thread has read the sub-histograms: the table scratch may overwrite them
+        FLIC_PHASE(2)  // histogram reduce, flat channels
 
         // ---- C. code table ------------------------------------------------------------------------------
         const uint32_t code_bits = cta_table(cnt, sm.u.t, sm.tab, sm.nib, tid);
@@ -1129,6 +1144,8 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
         if (one) size = (uint32_t)kBlkHdrWords1 + ((code_bits + 31u) >> 5);
         else if (!exact) size = (uint32_t)kBlkHdrWords + (code_bits >> 5) + (code_bits ? p.bha : 0u);
         if (!exact && tid == 0 && gb > 0) st_status(status + gb, ep | kStA | size);  // early: successors need not wait for the packing
+
+        FLIC_PHASE(3)  // code table
 
         // ---- D. pack the rows over the tile --------------------------------------------------------------
         {
@@ -1140,14 +1157,15 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
                 const int r = warp + kEncWarps * q;
                 uint32_t *trow = sm.tile + r * kStagePitch + kStagePad;
                 const int nv = r < (int)p.bha ? nvl : 0;
+                const bool full = lane_full && r < (int)p.bha;
                 uint32_t cur[C];
 #pragma unroll
                 for (int j = 0; j < C; ++j) cur[j] = nv ? trow[32 * j + lane] : 0u;
                 uint32_t qlo[C], qhi[C], ql[C], nbits = 0;
-                if (nv == 4 * C && flatmask == 0) {
+                if (full && flatmask == 0) {
 #pragma unroll
                     for (int j = 0; j < C; ++j) { ql[j] = quad_of<true, 0>(cur[j], 4 * j, 4 * C, 0u, sm.tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
-                } else if (nv == 4 * C && C == 4 && flatmask == 8u) {
+                } else if (full && C == 4 && flatmask == 8u) {
 #pragma unroll
                     for (int j = 0; j < C; ++j) { ql[j] = quad_of<true, 8>(cur[j], 4 * j, 4 * C, 8u, sm.tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
                 } else {
@@ -1175,6 +1193,7 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
             }
         }
         __syncthreads();
+        FLIC_PHASE(4)  // pack
 
         // ---- E. size, position (decoupled look-back), directory ---------------------------------------------
         if (warp == 0) {
@@ -1204,7 +1223,9 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
                 for (;;) {
                     unsigned long long v = 0;
                     if (j >= 0) {
-                        do { v = ld_status(status + j); } while ((v >> 42) != epoch || (v & (kStA | kStP)) == 0);
+                        // a predecessor that has not published yet is still building its table (or packing, with EXACT):
+                        // sleep instead of spinning, the issue slots are what the other CTAs of the SM are short of
+                        while (v = ld_status(status + j), (v >> 42) != epoch || (v & (kStA | kStP)) == 0) __nanosleep(64);
                     }
                     const uint32_t pmask = __ballot_sync(0xFFFFFFFFu, j >= 0 && (v & kStP) != 0);
                     const int stop = pmask ? __ffs(pmask) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
@@ -1230,6 +1251,7 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
             }
         }
         __syncthreads();
+        FLIC_PHASE(5)  // look-back
         size = sm.s_size;
         const uint32_t used = sm.s_used;
         const unsigned long long base = (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + sm.s_excl;
@@ -1299,7 +1321,9 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
                 for (uint32_t i = j; i < cntw; i += 8) o[i] = src[i];
             }
         }
+        FLIC_PHASE(6)  // copy-out (this thread's share)
     }
+#undef FLIC_PHASE
 }
 
 // Grid: resident CTAs only (the loop is persistent); correctness does not depend on co-residency, because a
@@ -1319,14 +1343,15 @@ static unsigned fused_grid(uint64_t total) {
 
 unsigned launch_encode_fused(const uint8_t *d_pixels, const Geo &g, uint32_t *d_streams, uint64_t capacity_words,
                              unsigned long long *d_dirE, unsigned long long *d_status, unsigned long long *d_ticket,
-                             unsigned long long ticket_base, uint32_t epoch, uint32_t *d_err, cudaStream_t s) {
+                             unsigned long long ticket_base, uint32_t epoch, uint32_t *d_err, unsigned long long *d_phase_clk,
+                             cudaStream_t s) {
     const uint64_t total = (uint64_t)g.n * g.nb;
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) && g.c >= 3;
     const PackMul pm = {1u << 8, 1u << 10, 1u << 18, 1u << 26};
     unsigned grid = 0;
 #define FLIC_ENC(C, SG) \
     (grid = fused_grid<C, SG>(total), \
-     k_encode<C, SG><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_streams, capacity_words, d_dirE, d_status, d_ticket, ticket_base, epoch, d_err, pm))
+     k_encode<C, SG><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_streams, capacity_words, d_dirE, d_status, d_ticket, ticket_base, epoch, d_err, pm, d_phase_clk))
     switch (g.c) {
         case 1: FLIC_ENC(1, false); break;
         case 2: FLIC_ENC(2, false); break;

@@ -1,16 +1,23 @@
 """Multi-GPU partitioning for the two ways the path shards (BASELINE.json north_star):
 
 * a batch of independent images: contiguous slices per rank, no data-path collective;
-* one oversized image: whole block rows per rank, then ONE tiny all-gather of the
-  per-rank stream byte counts, after which every rank knows where its payload lands
-  and rank 0 splices (directory rebase + payload concatenation).
+* one oversized image: whole block rows per rank, then ONE tiny all-gather of the per-rank part sizes,
+  after which every rank knows where its directory entries and payload land in the spliced stream and
+  sends them straight there; rank 0 finishes the splice (header + directory rebase).
 
-Works on any torch.distributed backend (NCCL on GPUs; gloo in the CPU tests).
-The encode function is injected so the host logic is testable without a GPU.
+Two implementations of the second path:
+
+* `encode_image_sharded` — host logic over any torch.distributed backend (gloo in the CPU tests), with
+  the encode and splice functions injected so it is testable without a GPU;
+* `ShardedImageCodec` — the device path used by bench.py's C4 line: parts never leave HBM, the
+  payloads travel by NCCL send/recv (NVLink) directly into their final position, and the directory
+  rebase runs as a kernel (`flic_splice_finish_device` / `flic_split_finish_device`).
 """
 import numpy as np
 
-from .codec import BLOCK_H
+from .codec import BLOCK_H, BLOCK_W, splice_plan
+
+HEADER_BYTES = 32
 
 
 def batch_slice(n_images, rank, world):
@@ -58,3 +65,119 @@ def encode_image_sharded(image, encode_fn, splice_fn, dist=None, device="cpu"):
         return None
     parts = [gathered[r][: counts[r]].cpu().numpy() for r in range(world) if counts[r]]
     return splice_fn(parts)
+
+
+class ShardedImageCodec:
+    """One w x h x c image split by block rows over the ranks of a NCCL process group; everything stays in HBM.
+
+    encode(rows): this rank's pixel rows [1, rows, w, c] (CUDA uint8) -> the spliced stream of the whole image
+        on rank 0 (a view into a preallocated buffer; None elsewhere).  Steps: the engine encodes the part;
+        the (n_blocks, payload_words) pairs are all-gathered (the only collective: 16 bytes per rank); every
+        rank sends its directory entries and its payload to rank 0, which receives them at the positions
+        flic_splice_plan gives — no staging copy; rank 0 runs flic_splice_finish_device.
+    decode(stream): the inverse — rank 0 cuts the directory at block-row boundaries and sends each rank its
+        entries and payload; every rank finishes its part stream (flic_split_finish_device) and decodes its
+        rows into its own [1, rows, w, c] tensor.
+    Every rank must call both with the same geometry.  world == 1 degenerates to plain encode / decode.
+    """
+
+    def __init__(self, codec, w, h, c, flags, dist=None, rank=0, world=1, device="cuda"):
+        import torch
+
+        self.torch, self.codec, self.dist = torch, codec, dist
+        self.w, self.h, self.c, self.flags, self.rank, self.world = w, h, c, flags, rank, world
+        self.rows = [block_row_slice(h, r, world) for r in range(world)]
+        self.y0, self.y1 = self.rows[rank]
+        self.nbx = (w + BLOCK_W - 1) // BLOCK_W
+        self.nbs = [self.nbx * ((b - a + BLOCK_H - 1) // BLOCK_H) for a, b in self.rows]
+        my_rows = max(self.y1 - self.y0, 1)
+        from .codec import max_stream_bytes
+        self.part = torch.empty(max_stream_bytes(w, my_rows, c), dtype=torch.uint8, device=device)
+        self.part_off = torch.zeros(2, dtype=torch.int64, device=device)
+        self.full = torch.empty(max_stream_bytes(w, h, c), dtype=torch.uint8, device=device) if rank == 0 else None
+        self.mine = torch.zeros(2, dtype=torch.int64, device=device)
+        self.counts = torch.zeros((world, 2), dtype=torch.int64, device=device)
+        self.pws = None        # payload words of every part (set by encode, or by decode on rank 0 and broadcast)
+        self.out = torch.empty((1, my_rows, w, c), dtype=torch.uint8, device=device)
+
+    def _exchange(self, ops):
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def encode(self, rows, stream=0):
+        torch, dist = self.torch, self.dist
+        self.codec.encode_batch_device(rows, self.part, self.part_off, self.flags, stream)
+        if self.world == 1:
+            n = int(self.part_off[1])
+            self.pws = [(n - HEADER_BYTES - 4 * (self.nbs[0] + 1)) // 4]
+            return self.part[:n]
+        hdr = self.part[:HEADER_BYTES].view(torch.int32)
+        self.mine.copy_(hdr[5:7])                         # (n_blocks, payload_words) of this part, on the device
+        self.mine.bitwise_and_(0xFFFFFFFF)                # the header words are unsigned
+        dist.all_gather_into_tensor(self.counts.view(-1), self.mine)   # the tiny all-gather
+        counts = self.counts.cpu().tolist()               # every rank needs the sizes to address its sends
+        nbs, pws = [int(x[0]) for x in counts], [int(x[1]) for x in counts]
+        assert nbs == self.nbs, (nbs, self.nbs)
+        self.pws = pws
+        doff, poff, total = splice_plan(nbs, pws)
+        r = self.rank
+        my_dir = self.part[HEADER_BYTES: HEADER_BYTES + 4 * nbs[r]]
+        my_pay = self.part[HEADER_BYTES + 4 * (nbs[r] + 1): HEADER_BYTES + 4 * (nbs[r] + 1) + 4 * pws[r]]
+        ops = []
+        if r == 0:
+            self.full[doff[0]: doff[0] + 4 * nbs[0]].copy_(my_dir)
+            self.full[poff[0]: poff[0] + 4 * pws[0]].copy_(my_pay)
+            for q in range(1, self.world):
+                ops.append(dist.P2POp(dist.irecv, self.full[doff[q]: doff[q] + 4 * nbs[q]], q))
+                if pws[q]:
+                    ops.append(dist.P2POp(dist.irecv, self.full[poff[q]: poff[q] + 4 * pws[q]], q))
+        else:
+            ops.append(dist.P2POp(dist.isend, my_dir, 0))
+            if pws[r]:
+                ops.append(dist.P2POp(dist.isend, my_pay, 0))
+        self._exchange(ops)
+        if r != 0:
+            return None
+        self.codec.splice_finish_device(self.full, nbs, pws, self.w, self.h, self.c, self.flags, stream)
+        return self.full[:total]
+
+    def decode(self, stream_full=None, stream=0):
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            off = torch.tensor([0, stream_full.numel()], dtype=torch.int64, device=stream_full.device)
+            self.codec.decode_batch_device(stream_full, off, self.out, self.flags, stream)
+            return self.out
+        nbs = self.nbs
+        k = self.world
+        first = np.concatenate([[0], np.cumsum(nbs)]).astype(np.int64)   # first block of every part
+        # rank 0 reads the directory at the k+1 part boundaries and tells everybody (the tiny collective of decode)
+        bounds = torch.zeros(k + 1, dtype=torch.int64, device=self.part.device)
+        if self.rank == 0:
+            dirw = stream_full[HEADER_BYTES: HEADER_BYTES + 4 * (int(first[-1]) + 1)].view(torch.int32)
+            idx = torch.from_numpy(first).to(self.part.device)
+            bounds.copy_(dirw[idx].to(torch.int64) & 0xFFFFFFFF)
+        dist.broadcast(bounds, 0)
+        b = bounds.cpu().tolist()
+        pws = [int(b[i + 1] - b[i]) for i in range(k)]
+        pay0 = HEADER_BYTES + 4 * (int(first[-1]) + 1)
+        r = self.rank
+        my_dir = self.part[HEADER_BYTES: HEADER_BYTES + 4 * (nbs[r] + 1)]
+        my_pay = self.part[HEADER_BYTES + 4 * (nbs[r] + 1): HEADER_BYTES + 4 * (nbs[r] + 1) + 4 * pws[r]]
+        ops = []
+        if r == 0:
+            for q in range(1, k):
+                ops.append(dist.P2POp(dist.isend, stream_full[HEADER_BYTES + 4 * int(first[q]): HEADER_BYTES + 4 * (int(first[q + 1]) + 1)], q))
+                if pws[q]:
+                    ops.append(dist.P2POp(dist.isend, stream_full[pay0 + 4 * int(b[q]): pay0 + 4 * int(b[q + 1])], q))
+            my_dir.copy_(stream_full[HEADER_BYTES: HEADER_BYTES + 4 * (nbs[0] + 1)])
+            my_pay.copy_(stream_full[pay0: pay0 + 4 * pws[0]])
+        else:
+            ops.append(dist.P2POp(dist.irecv, my_dir, 0))
+            if pws[r]:
+                ops.append(dist.P2POp(dist.irecv, my_pay, 0))
+        self._exchange(ops)
+        self.codec.split_finish_device(self.part, self.w, self.y1 - self.y0, self.c, self.flags, stream)
+        self.part_off[1] = HEADER_BYTES + 4 * (nbs[r] + 1) + 4 * pws[r]
+        self.codec.decode_batch_device(self.part, self.part_off, self.out, self.flags, stream)
+        return self.out

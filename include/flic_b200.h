@@ -71,14 +71,19 @@ const char *flic_strerror(int code);
 const char *flic_last_error(const flic_ctx *ctx); /* detail of the last FLIC_E_CUDA / _INTERNAL */
 int flic_version(void);
 
-/* Options.  FLIC_OPT_ENCODER selects the encode path for plain FLP0 v3 streams: the fused single-pass
- * kernel (default: pixels are read once, residuals never leave the SM) or the round-1 staged pipeline
- * (five kernels with a residual plane in HBM; kept for A/B measurements).  Both produce identical bytes.
+/* Options.  FLIC_OPT_ENCODER selects the encode path for plain FLP0 v3 streams; both produce identical bytes.
+ *   FUSED   one persistent kernel: pixels are read once, residuals never leave the SM, blocks are placed by a
+ *           decoupled look-back (2 launches per call, DRAM traffic = the algorithmic bytes);
+ *   STAGED  the five-kernel pipeline with a residual plane in HBM (2.4x the algorithmic DRAM bytes, but every
+ *           stage runs at full occupancy and the serial Huffman merges of eight blocks share a warp — on B200
+ *           this path is bound by issue slots, not by HBM, and is the faster one for large batches);
+ *   AUTO    (default) FUSED for small jobs, where launch count and latency matter, STAGED for large ones.
  * FLIC_FLAG_ONE_STREAM / FLIC_FLAG_EXACT streams always take the fused kernel.  The environment variable
- * FLIC_ENCODER=staged sets the same default at flic_create(). */
+ * FLIC_ENCODER=fused|staged|auto sets the default at flic_create(). */
 #define FLIC_OPT_ENCODER 1
 #define FLIC_ENCODER_FUSED 0
 #define FLIC_ENCODER_STAGED 1
+#define FLIC_ENCODER_AUTO 2
 int flic_set_option(flic_ctx *ctx, int option, int value);
 
 /* ---- size queries ------------------------------------------------------ */
@@ -211,6 +216,13 @@ int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t n_blocks_t
  * since the previous call, and clears them. */
 int flic_set_kernel_timing(flic_ctx *ctx, int enable);
 int flic_get_kernel_times(flic_ctx *ctx, double ms[FLIC_K_COUNT], uint64_t counts[FLIC_K_COUNT]);
+
+/* Debug: when the context was created with FLIC_PHASE_CLOCKS=1 in the environment, thread 0 of every k_encode
+ * CTA accumulates the SM cycles it spent in each phase of a block (0 ticket+clear, 1 load+residuals+histogram,
+ * 2 histogram reduce, 3 code table, 4 pack, 5 look-back, 6 copy-out); this reads and clears the sums.
+ * FLIC_E_UNSUPPORTED otherwise (the kernel then carries a null pointer and measures nothing). */
+#define FLIC_PHASES 8
+int flic_get_phase_clocks(flic_ctx *ctx, uint64_t cycles[FLIC_PHASES]);
 
 /* Number of kernel launches issued through ctx since creation (bench.py's gpu_launches). */
 uint64_t flic_launch_count(const flic_ctx *ctx);

@@ -21,12 +21,18 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+@pytest.fixture(autouse=True)
+def _default_encoder_after_each_test(codec):
+    yield
+    codec.set_encoder("auto")
+
+
 @pytest.fixture(params=["fused", "staged"])
 def encoder(request, codec):
     """Both encode paths (the fused single-pass kernel and the round-1 staged pipeline) must emit the same bytes."""
     codec.set_encoder(request.param)
     yield request.param
-    codec.set_encoder("fused")
+    codec.set_encoder("auto")
 
 
 @pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
@@ -63,12 +69,13 @@ def test_staged_encoder_bytes(codec, oracle, name, build, flags):
         img = build()
         assert np.array_equal(codec.encode(img, flags), oracle.encode(img, flags))
     finally:
-        codec.set_encoder("fused")
+        codec.set_encoder("auto")
 
 
 @pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
 @pytest.mark.parametrize("flags", cases.ALL_FLAGS)
 def test_encode_bytes_and_decode_pixels(codec, oracle, name, build, flags):
+    codec.set_encoder("fused")
     img = build()
     want = oracle.encode(img, flags)
     got = codec.encode(img, flags)

@@ -74,3 +74,81 @@ def test_block_row_split_world2(flic, oracle, shape):
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert all(ok for _, ok, _ in res), res
+
+
+# ---- the device path's host logic (ShardedImageCodec) on CPU tensors over gloo, with the engine replaced by the model
+class _ModelCodec:
+    """Stand-in for flic_b200.Codec on CPU tensors: exactly the calls ShardedImageCodec makes, answered by the CPU
+    model (encode / decode) and by numpy restatements of the two finish kernels."""
+
+    def __init__(self, orc):
+        self.orc = orc
+
+    def encode_batch_device(self, px, streams, off, flags, stream=0):
+        s = self.orc.encode(px[0].numpy(), flags)
+        streams[: s.size] = torch.from_numpy(s)
+        off[0], off[1] = 0, int(s.size)
+
+    def decode_batch_device(self, streams, off, out, flags, stream=0):
+        n = int(off[1])
+        out[0] = torch.from_numpy(self.orc.decode(streams[:n].numpy(), tuple(out.shape[1:])))
+
+    @staticmethod
+    def _header(w, h, c, flags, nb, pw):
+        return np.array([0x30504C46, 3 | (c << 16) | (flags << 24), w, h, 128 | (32 << 16), nb, pw, 10], dtype=np.uint32)
+
+    def splice_finish_device(self, out, nbs, pws, w, h, c, flags, stream=0):
+        o = out.numpy().view(np.uint32)
+        nb, pw = sum(nbs), sum(pws)
+        first, base = 0, 0
+        for n, p in zip(nbs, pws):
+            o[8 + first: 8 + first + n] += np.uint32(base)
+            first += n; base += p
+        o[8 + nb] = pw
+        o[:8] = self._header(w, h, c, flags, nb, pw)
+
+    def split_finish_device(self, part, w, h, c, flags, stream=0):
+        o = part.numpy().view(np.uint32)
+        nb = -(-w // 128) * -(-h // 32)
+        first = int(o[8])
+        o[8: 8 + nb + 1] -= np.uint32(first)
+        o[:8] = self._header(w, h, c, flags, nb, int(o[8 + nb]))
+
+
+def _worker_dev(rank, world, port, shape, flags, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import flic_b200 as flic
+        import oracle_binding
+        orc = oracle_binding.Oracle(os.path.join(ROOT, "oracle", "libflp0_oracle.so"))
+        h, w, c = shape
+        img = cases.gradient(w, h, c, 78)
+        sc = flic.sharding.ShardedImageCodec(_ModelCodec(orc), w, h, c, flags, dist, rank, world, device="cpu")
+        rows = torch.from_numpy(img[sc.y0: sc.y1][None].copy())
+        full = sc.encode(rows)
+        ok = True
+        if rank == 0:
+            ok = bool(np.array_equal(full.numpy(), orc.encode(img, flags)))
+        out = sc.decode(full)
+        ok = ok and bool(np.array_equal(out[0].numpy(), img[sc.y0: sc.y1]))
+        q.put(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,flags", [((200, 300, 3), 0x01), ((96, 130, 4), 0x21), ((70, 64, 1), 0x41)])
+def test_sharded_codec_exchange_world2(flic, oracle, shape, flags):
+    """encode: parts -> all-gather of (n_blocks, payload_words) -> sends straight into the spliced stream -> finish;
+    decode: directory cut at block-row boundaries -> sends -> finish -> per-rank rows.  Spliced bytes == the model's
+    encode of the whole image; every rank gets its rows back."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_dev, args=(r, 2, port, shape, flags, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(2)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert all(res), res
