@@ -43,7 +43,7 @@ WORKLOADS = {
     "C2x64": ("C2", 64),  # configs[1] geometry (3840x2160 RGBA8) batched so a step exceeds L2 (2.1 GB raw)
     "C2x8": ("C2", 8),    # same geometry, 265 MB/step: short enough to profile under ncu, still > L2
     "C2Ax64": ("C2A", 64),  # the same batch with a gradient alpha plane (no flat channel: four symbols per pixel)
-    "C1": ("C1", 1), "C2": ("C2", 1), "C3": ("C3", 128), "C4": ("C4", 1), "C5": ("C5", 64),
+    "C1": ("C1", 1), "C2": ("C2", 1), "C3": ("C3", 128), "C4": ("C4", 1), "C5": ("C5", 64), "C5x8": ("C5", 8),
     "C3full": ("C3", 1024),  # configs[2] at its full size on ONE GPU: 6.4 GB raw per step
 }
 

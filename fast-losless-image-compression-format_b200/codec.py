@@ -292,8 +292,9 @@ class Codec:
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNELS)}
 
     def phase_clocks(self):
-        """Per-phase SM-cycle sums of k_encode since the last call (needs FLIC_PHASE_CLOCKS=1 at creation)."""
-        cyc = (C.c_uint64 * 8)()
+        """Per-phase SM-cycle sums of k_encode [0:8] and k_decode_one [8:16] since the last call (needs
+        FLIC_PHASE_CLOCKS=1 at creation)."""
+        cyc = (C.c_uint64 * 16)()
         self._chk(self.lib.flic_get_phase_clocks(self.h, cyc))
         return [int(x) for x in cyc]
 

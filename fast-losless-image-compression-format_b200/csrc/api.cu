@@ -23,13 +23,22 @@ namespace {
 // streams with double-buffered device buffers, so PCIe in, compute and PCIe out overlap.  Encode and decode
 // own separate pipes, so an encode call and a decode call (flic_*_submit) can be in flight together and use
 // both directions of the link at once.
+// kDepth chunks are in flight per direction.  The copy engines are FIFOs shared by everything on the device, so a
+// copy that is enqueued before its inputs are ready (a stream-wait on a kernel's event in front of it) stalls every
+// copy behind it — including the other call's when an encode and a decode are in flight together (measured: both
+// calls together took exactly the sum of the two alone, while the bare link carries both patterns at once in 0.8 of
+// that).  Hence the rule in both pipelines below: A COPY IS ISSUED ONLY WHEN IT CAN START — the host has already
+// seen the event it depends on — and stream sizes come back through mapped pinned memory the kernels write to,
+// not through a device-to-host copy queued behind the kernels.
+constexpr int kDepth = 4;
 struct Pipe {
-    uint8_t *d_pix[2] = {nullptr, nullptr}, *d_str[2] = {nullptr, nullptr};
-    unsigned long long *d_off[2] = {nullptr, nullptr};
-    unsigned long long *h_off[2] = {nullptr, nullptr};  // pinned, off_cap entries each
+    uint8_t *d_pix[kDepth] = {}, *d_str[kDepth] = {};
+    unsigned long long *d_off[kDepth] = {};
+    unsigned long long *h_off[kDepth] = {};  // pinned + mapped, off_cap entries each
+    unsigned long long *m_off[kDepth] = {};  // the device's view of h_off (encode kernels write their offsets straight to the host)
     uint64_t pix_cap = 0, str_cap = 0, off_cap = 0;
     cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;  // kernels / H2D / D2H
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[kDepth] = {}, ev_k[kDepth] = {}, ev_out[kDepth] = {};
     // submit/wait
     std::thread worker;
     bool busy = false;
@@ -151,9 +160,11 @@ static cudaError_t pipe_create(Pipe &p) {
     cudaError_t e = cudaStreamCreateWithFlags(&p.s_k, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    for (int i = 0; i < kDepth && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&p.ev_in[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.ev_k[i], cudaEventDisableTiming);
+        // the host waits on ev_k once per chunk: a blocking (not spinning) wait, so that the other call's worker thread
+        // is not starved of the driver while this one waits
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.ev_k[i], cudaEventDisableTiming | cudaEventBlockingSync);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.ev_out[i], cudaEventDisableTiming);
     }
     return e;
@@ -161,7 +172,7 @@ static cudaError_t pipe_create(Pipe &p) {
 
 static void pipe_destroy(Pipe &p) {
     if (p.worker.joinable()) p.worker.join();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kDepth; ++i) {
         cudaFree(p.d_pix[i]); cudaFree(p.d_str[i]); cudaFree(p.d_off[i]);
         if (p.h_off[i]) cudaFreeHost(p.h_off[i]);
         if (p.ev_in[i]) cudaEventDestroy(p.ev_in[i]);
@@ -194,8 +205,8 @@ extern "C" int flic_create(int device, flic_ctx **out) {
     if (e == cudaSuccess) e = cudaMemset(ctx->d_ticket, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_err, 4 * sizeof(uint32_t));
     if (e == cudaSuccess && getenv("FLIC_PHASE_CLOCKS")) {
-        e = cudaMalloc(&ctx->d_phase, FLIC_PHASES * sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMemset(ctx->d_phase, 0, FLIC_PHASES * sizeof(unsigned long long));
+        e = cudaMalloc(&ctx->d_phase, 2 * FLIC_PHASES * sizeof(unsigned long long));  // k_encode, then k_decode_one
+        if (e == cudaSuccess) e = cudaMemset(ctx->d_phase, 0, 2 * FLIC_PHASES * sizeof(unsigned long long));
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_ws, cudaEventDisableTiming);
     if (e == cudaSuccess) e = pipe_create(ctx->enc);
@@ -392,7 +403,8 @@ extern "C" int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams,
     CU(cudaSetDevice(ctx->device));
     if (flags & FLIC_FLAG_ONE_STREAM) {
         KernelTimer t(ctx, FLIC_K_DECODE_ONE, (cudaStream_t)stream);
-        launch_decode_one((const uint32_t *)d_streams, (const unsigned long long *)d_offsets, g, d_pixels, ctx->d_err + 1, (cudaStream_t)stream);
+        launch_decode_one((const uint32_t *)d_streams, (const unsigned long long *)d_offsets, g, d_pixels, ctx->d_err + 1,
+                          ctx->d_phase ? ctx->d_phase + FLIC_PHASES : nullptr, (cudaStream_t)stream);
     } else {
         KernelTimer t(ctx, FLIC_K_DECODE, (cudaStream_t)stream);
         alignas(64) CUtensorMap tm;
@@ -446,13 +458,13 @@ static int check_word(flic_ctx *ctx, int word, cudaStream_t s) {
     return report_device_errors(ctx, ctx->h_err[word]);
 }
 
-extern "C" int flic_get_phase_clocks(flic_ctx *ctx, uint64_t cycles[FLIC_PHASES]) {
+extern "C" int flic_get_phase_clocks(flic_ctx *ctx, uint64_t cycles[2 * FLIC_PHASES]) {
     if (!ctx || !cycles) return FLIC_E_ARG;
     if (!ctx->d_phase) return FLIC_E_UNSUPPORTED;  // the context was created without FLIC_PHASE_CLOCKS=1
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(cycles, ctx->d_phase, FLIC_PHASES * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CU(cudaMemset(ctx->d_phase, 0, FLIC_PHASES * sizeof(unsigned long long)));
+    CU(cudaMemcpy(cycles, ctx->d_phase, 2 * FLIC_PHASES * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemset(ctx->d_phase, 0, 2 * FLIC_PHASES * sizeof(unsigned long long)));
     return FLIC_OK;
 }
 
@@ -523,27 +535,28 @@ struct AutoPin {
 
 static int ensure_staging(flic_ctx *ctx, Pipe &p, uint64_t pix, uint64_t str, uint64_t noff) {
     if (pix > p.pix_cap) {
-        for (int i = 0; i < 2; ++i) { cudaFree(p.d_pix[i]); p.d_pix[i] = nullptr; }
+        for (int i = 0; i < kDepth; ++i) { cudaFree(p.d_pix[i]); p.d_pix[i] = nullptr; }
         p.pix_cap = 0;
-        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&p.d_pix[i], pix));
+        for (int i = 0; i < kDepth; ++i) CU(cudaMalloc(&p.d_pix[i], pix));
         p.pix_cap = pix;
     }
     if (str > p.str_cap) {
-        for (int i = 0; i < 2; ++i) { cudaFree(p.d_str[i]); p.d_str[i] = nullptr; }
+        for (int i = 0; i < kDepth; ++i) { cudaFree(p.d_str[i]); p.d_str[i] = nullptr; }
         p.str_cap = 0;
-        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&p.d_str[i], str + 16));
+        for (int i = 0; i < kDepth; ++i) CU(cudaMalloc(&p.d_str[i], str + 16));
         p.str_cap = str;
     }
     if (noff > p.off_cap) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kDepth; ++i) {
             cudaFree(p.d_off[i]); p.d_off[i] = nullptr;
             if (p.h_off[i]) cudaFreeHost(p.h_off[i]);
             p.h_off[i] = nullptr;
         }
         p.off_cap = 0;
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kDepth; ++i) {
             CU(cudaMalloc(&p.d_off[i], noff * sizeof(unsigned long long)));
-            CU(cudaMallocHost(&p.h_off[i], noff * sizeof(unsigned long long)));
+            CU(cudaHostAlloc(&p.h_off[i], noff * sizeof(unsigned long long), cudaHostAllocMapped));
+            CU(cudaHostGetDevicePointer(&p.m_off[i], p.h_off[i], 0));
         }
         p.off_cap = noff;
     }
@@ -579,39 +592,51 @@ static int encode_batch_impl(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n,
     const uint32_t chunks = (n + m - 1) / m;
     uint64_t out_pos = 0;
     h_offsets[0] = 0;
-    // software pipeline: H2D(k+1) is issued before the host waits for the sizes of chunk k
-    auto issue_in = [&](uint32_t k) -> int {
-        const int b = k & 1;
+    // Software pipeline over chunks, three host stages per chunk:
+    //   A  H2D of the chunk's pixels — issued once the host has seen the kernels of the chunk that last used the
+    //      staging buffer finish, up to kDepth chunks ahead of the kernels
+    //   B  kernels (their wait for the H2D is on the compute queue, where it stalls nobody else); the stream
+    //      offsets land in mapped pinned memory
+    //   C  wait for the kernels, place the chunk in the caller's buffer, D2H of exactly that many bytes
+    uint32_t issued_in = 0;
+    auto stage_a = [&]() -> int {
+        const uint32_t k = issued_in++;
+        const int b = k % kDepth;
         const uint32_t first = k * m, cnt = (first + m <= n) ? m : n - first;
-        if (k >= 2) CU(cudaStreamWaitEvent(P.s_in, P.ev_k[b], 0));  // kernels of chunk k-2 have consumed d_pix[b]
         CU(cudaMemcpyAsync(P.d_pix[b], h_pixels + (uint64_t)first * img_bytes, cnt * img_bytes, cudaMemcpyHostToDevice, P.s_in));
         CU(cudaEventRecord(P.ev_in[b], P.s_in));
         return FLIC_OK;
     };
-    rc = issue_in(0);
-    for (uint32_t k = 0; k < chunks && rc == FLIC_OK; ++k) {
-        const int b = k & 1;
+    auto stage_b = [&](uint32_t k) -> int {
+        const int b = k % kDepth;
         const uint32_t first = k * m, cnt = (first + m <= n) ? m : n - first;
-        rc = [&]() -> int {
-            CU(cudaStreamWaitEvent(P.s_k, P.ev_in[b], 0));
-            if (k >= 2) CU(cudaStreamWaitEvent(P.s_k, P.ev_out[b], 0));  // D2H of chunk k-2 has drained d_str[b]
-            int r = flic_encode_batch_device(ctx, P.d_pix[b], cnt, w, h, c, flags, P.d_str[b], cnt * img_worst,
-                                             (uint64_t *)P.d_off[b], P.s_k);
-            if (r) return r;
-            CU(cudaMemcpyAsync(P.h_off[b], P.d_off[b], ((uint64_t)cnt + 1) * 8, cudaMemcpyDeviceToHost, P.s_k));
-            CU(cudaEventRecord(P.ev_k[b], P.s_k));
-            if (k + 1 < chunks) { r = issue_in(k + 1); if (r) return r; }
-            CU(cudaEventSynchronize(P.ev_k[b]));
-            const uint64_t total = P.h_off[b][cnt];
-            if (total > cnt * img_worst) return FLIC_E_INTERNAL;  // kernels flagged a capacity overrun
-            if (out_pos + total > capacity_bytes) return FLIC_E_CAPACITY;
-            for (uint32_t i = 1; i <= cnt; ++i) h_offsets[first + i] = out_pos + P.h_off[b][i];
-            CU(cudaStreamWaitEvent(P.s_out, P.ev_k[b], 0));
-            CU(cudaMemcpyAsync(h_streams + out_pos, P.d_str[b], total, cudaMemcpyDeviceToHost, P.s_out));
-            CU(cudaEventRecord(P.ev_out[b], P.s_out));
-            out_pos += total;
-            return FLIC_OK;
-        }();
+        CU(cudaStreamWaitEvent(P.s_k, P.ev_in[b], 0));
+        if (k >= (uint32_t)kDepth) CU(cudaStreamWaitEvent(P.s_k, P.ev_out[b], 0));  // D2H of chunk k-kDepth has drained d_str[b]
+        int r = flic_encode_batch_device(ctx, P.d_pix[b], cnt, w, h, c, flags, P.d_str[b], cnt * img_worst, (uint64_t *)P.m_off[b], P.s_k);
+        if (r) return r;
+        CU(cudaEventRecord(P.ev_k[b], P.s_k));
+        return FLIC_OK;
+    };
+    auto stage_c = [&](uint32_t k) -> int {
+        const int b = k % kDepth;
+        const uint32_t first = k * m, cnt = (first + m <= n) ? m : n - first;
+        CU(cudaEventSynchronize(P.ev_k[b]));
+        const uint64_t total = P.h_off[b][cnt];
+        if (total > cnt * img_worst) return FLIC_E_INTERNAL;  // kernels flagged a capacity overrun
+        if (out_pos + total > capacity_bytes) return FLIC_E_CAPACITY;
+        for (uint32_t i = 1; i <= cnt; ++i) h_offsets[first + i] = out_pos + P.h_off[b][i];
+        CU(cudaMemcpyAsync(h_streams + out_pos, P.d_str[b], total, cudaMemcpyDeviceToHost, P.s_out));  // its kernels are done: runnable now
+        CU(cudaEventRecord(P.ev_out[b], P.s_out));
+        out_pos += total;
+        return FLIC_OK;
+    };
+    while (rc == FLIC_OK && issued_in < chunks && issued_in < (uint32_t)kDepth) rc = stage_a();  // every staging buffer is free
+    for (uint32_t step = 0; step <= chunks && rc == FLIC_OK; ++step) {
+        if (step < chunks) rc = stage_b(step);
+        if (rc == FLIC_OK && step >= 1) {
+            rc = stage_c(step - 1);
+            if (rc == FLIC_OK && issued_in < chunks) rc = stage_a();  // the kernels of chunk step-1 are done: its pixel buffer is free
+        }
     }
     drain(P);  // success or not: nothing may touch the caller's buffers after the call returns
     const int chk = check_word(ctx, 0, P.s_k);
@@ -671,28 +696,37 @@ static int decode_run(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h
     }
     int rc = ensure_staging(ctx, P, m * img_bytes, max_str, (uint64_t)m + 1);
     if (rc) return rc;
-    for (uint32_t k = 0; k < chunks && rc == FLIC_OK; ++k) {
-        const int b = k & 1;
+    // Same rule as the encoder's pipeline: the H2D of a chunk is issued when the host has seen the kernel that last
+    // read the staging buffer finish; the D2H of a chunk is issued when the host has seen its kernel finish.
+    auto issue = [&](uint32_t k) -> int {
+        const int b = k % kDepth;
         const uint32_t f0 = lo + k * m, cnt = (f0 + m <= hi) ? m : hi - f0;
         const uint64_t base = h_offsets[f0], sz = h_offsets[f0 + cnt] - base;
-        rc = [&]() -> int {
-            // the pinned offsets and d_str[b] of chunk k-2 must have been consumed by its kernel
-            if (k >= 2) CU(cudaEventSynchronize(P.ev_k[b]));
-            for (uint32_t i = 0; i <= cnt; ++i) P.h_off[b][i] = h_offsets[f0 + i] - base;
-            CU(cudaMemcpyAsync(P.d_str[b], h_streams + base, sz, cudaMemcpyHostToDevice, P.s_in));
-            CU(cudaMemcpyAsync(P.d_off[b], P.h_off[b], ((uint64_t)cnt + 1) * 8, cudaMemcpyHostToDevice, P.s_in));
-            CU(cudaEventRecord(P.ev_in[b], P.s_in));
-            CU(cudaStreamWaitEvent(P.s_k, P.ev_in[b], 0));
-            if (k >= 2) CU(cudaStreamWaitEvent(P.s_k, P.ev_out[b], 0));  // D2H of chunk k-2 has drained d_pix[b]
-            int r = flic_decode_batch_device(ctx, P.d_str[b], (const uint64_t *)P.d_off[b], cnt, g0.width, g0.height,
-                                             g0.channels, g0.flags, P.d_pix[b], P.s_k);
-            if (r) return r;
-            CU(cudaEventRecord(P.ev_k[b], P.s_k));
-            CU(cudaStreamWaitEvent(P.s_out, P.ev_k[b], 0));
-            CU(cudaMemcpyAsync(h_pixels + (uint64_t)(f0 - lo) * img_bytes, P.d_pix[b], cnt * img_bytes, cudaMemcpyDeviceToHost, P.s_out));
-            CU(cudaEventRecord(P.ev_out[b], P.s_out));
-            return FLIC_OK;
-        }();
+        for (uint32_t i = 0; i <= cnt; ++i) P.h_off[b][i] = h_offsets[f0 + i] - base;
+        CU(cudaMemcpyAsync(P.d_str[b], h_streams + base, sz, cudaMemcpyHostToDevice, P.s_in));
+        CU(cudaMemcpyAsync(P.d_off[b], P.h_off[b], ((uint64_t)cnt + 1) * 8, cudaMemcpyHostToDevice, P.s_in));
+        CU(cudaEventRecord(P.ev_in[b], P.s_in));
+        CU(cudaStreamWaitEvent(P.s_k, P.ev_in[b], 0));
+        if (k >= (uint32_t)kDepth) CU(cudaStreamWaitEvent(P.s_k, P.ev_out[b], 0));  // D2H of chunk k-kDepth has drained d_pix[b]
+        int r = flic_decode_batch_device(ctx, P.d_str[b], (const uint64_t *)P.d_off[b], cnt, g0.width, g0.height, g0.channels,
+                                         g0.flags, P.d_pix[b], P.s_k);
+        if (r) return r;
+        CU(cudaEventRecord(P.ev_k[b], P.s_k));
+        return FLIC_OK;
+    };
+    auto retire = [&](uint32_t k) -> int {
+        const int b = k % kDepth;
+        const uint32_t f0 = lo + k * m, cnt = (f0 + m <= hi) ? m : hi - f0;
+        CU(cudaEventSynchronize(P.ev_k[b]));  // the chunk's pixels exist: its D2H is runnable, its stream buffer is free
+        CU(cudaMemcpyAsync(h_pixels + (uint64_t)(f0 - lo) * img_bytes, P.d_pix[b], cnt * img_bytes, cudaMemcpyDeviceToHost, P.s_out));
+        CU(cudaEventRecord(P.ev_out[b], P.s_out));
+        return FLIC_OK;
+    };
+    uint32_t issued = 0;
+    while (rc == FLIC_OK && issued < chunks && issued < (uint32_t)kDepth) rc = issue(issued++);
+    for (uint32_t k = 0; k < chunks && rc == FLIC_OK; ++k) {
+        rc = retire(k);
+        if (rc == FLIC_OK && issued < chunks) rc = issue(issued++);
     }
     drain(P);
     return rc;

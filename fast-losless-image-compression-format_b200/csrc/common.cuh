@@ -205,7 +205,7 @@ unsigned launch_encode_fused(const uint8_t *d_pixels, const Geo &g, uint32_t *d_
 void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offsets, const Geo &g,
                    uint8_t *d_pixels, uint32_t *d_err, const void *tensor_map, cudaStream_t s);
 void launch_decode_one(const uint32_t *d_streams, const unsigned long long *d_offsets, const Geo &g,
-                       uint8_t *d_pixels, uint32_t *d_err, cudaStream_t s);
+                       uint8_t *d_pixels, uint32_t *d_err, unsigned long long *d_phase_clk, cudaStream_t s);
 
 // block-row splice on the device (splice.cu)
 struct SpliceParts {

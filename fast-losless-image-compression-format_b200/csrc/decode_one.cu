@@ -12,8 +12,12 @@
 //      sub-sequence, counts the symbols from there to the first boundary e past its end;
 //   2. the chain is consistent when every thread's b equals its predecessor's e.  A thread whose b is wrong
 //      decodes again from the predecessor's e; if that moves its own e, the next thread follows in the next
-//      round, until nothing moves (fixed-length-like codes, which never re-synchronise, need one round per
-//      sub-sequence: that is the price of this layout);
+//      round.  Typical codes settle in a round or two.  Near fixed-length codes (noise: lengths 7-9) take a
+//      hundred symbols or more to re-synchronise, so when a quarter of the links come out broken the chains are
+//      run again with a run-in of two whole sub-sequences before the rounds start.  (Measured alternative,
+//      dropped: tabulating every thread's sub-sequence from all kL possible entry offsets and walking the table
+//      — bounded time, but ten passes: 59 ms against 42 ms on the 64 x 4K noise batch.)  The worst case —
+//      codes of exactly one length, which never re-synchronise — degrades to one round per sub-sequence;
 //   3. a block-wide scan of the symbol counts gives every thread its first symbol index;
 //   4. every thread decodes its symbols once more from its true start into a DENSE residual buffer (symbol i
 //      at byte i: no per-symbol pixel bookkeeping);
@@ -37,7 +41,7 @@ template <int C>
 struct OneSmem {
     static constexpr int kMaxWords = kBH * ((kBW * C * kL + 31) / 32);  // longest legal block stream
     uint32_t sst[kMaxWords + 4];              // the block's stream, then zero words
-    uint8_t res[kBH * kBW * C + 64];          // residual bytes in symbol order (flat channels have none)
+    struct { uint8_t res[kBH * kBW * C + 64]; } u;  // residual bytes in symbol order (flat channels have none)
     uint16_t lut[kLutSize];
     LutScratch sc;
     uint32_t E[kOneThreads];                  // where each thread's chain ends = where the next one's starts
@@ -70,8 +74,17 @@ __device__ __forceinline__ void unpack4(int CS, const uint32_t *w, uint32_t (&px
 template <int C>
 __global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *__restrict__ streams,
                                                               const unsigned long long *__restrict__ offsets, Geo g,
-                                                              uint8_t *__restrict__ pixels, uint32_t *err) {
+                                                              uint8_t *__restrict__ pixels, uint32_t *err,
+                                                              unsigned long long *phase_clk) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    // phase_clk (debug, normally null): thread 0 of every CTA adds the cycles it spent per step
+    long long t_prev = phase_clk ? clock64() : 0;
+#define FLIC_PHASE(i)                                                       \
+    if (phase_clk && threadIdx.x == 0) {                                    \
+        const long long t_now = clock64();                                  \
+        atomicAdd(phase_clk + (i), (unsigned long long)(t_now - t_prev));   \
+        t_prev = t_now;                                                     \
+    }
     OneSmem<C> &sm = *reinterpret_cast<OneSmem<C> *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t gb = blockIdx.x;
@@ -102,10 +115,11 @@ __global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *_
     const uint32_t fmask = __ldg(blk + 32), fvals = __ldg(blk + 33);
 
     // ---- 0. stream -> shared memory; LUT
-    for (uint32_t i = tid; i < nw + 4; i += kOneThreads) sm.sst[i] = i < nw ? __ldg(blk + kBlkHdrWords1 + i) : 0u;
-    if (warp == 0) {
+    if (warp == 0) {  // one warp builds the LUT while the other seven fetch the stream
         const bool lut_ok = build_lut(sm.lut, sm.sc, __ldg(blk + lane), lane);
         if (lane == 0) sm.ok = lut_ok && (fmask >> C) == 0;
+    } else {
+        for (uint32_t i = tid - 32; i < nw + 4; i += kOneThreads - 32) sm.sst[i] = i < nw ? __ldg(blk + kBlkHdrWords1 + i) : 0u;
     }
     __syncthreads();
     if (!sm.ok) {
@@ -116,12 +130,13 @@ __global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *_
     const uint32_t nsym = p.bwa * p.bha * CS;
     const bool nobits = (sm.lut[0] & 0xFFu) == 0;           // one symbol with a zero-length code: every LUT entry is it
     const char *lutb = reinterpret_cast<const char *>(sm.lut);
+    FLIC_PHASE(0)  // stream copy + LUT
 
     if (nobits || nsym == 0) {
         // nothing to read: every coded byte is the sole symbol
         const uint32_t fill = (uint32_t)(sm.lut[0] >> 8) * 0x01010101u;
-        uint32_t *r32 = reinterpret_cast<uint32_t *>(sm.res);
-        for (int i = tid; i < (int)(sizeof sm.res / 4); i += kOneThreads) r32[i] = fill;
+        uint32_t *r32 = reinterpret_cast<uint32_t *>(sm.u.res);
+        for (int i = tid; i < (int)(sizeof sm.u.res / 4); i += kOneThreads) r32[i] = fill;
     } else {
         // an incomplete code (only a damaged table has one) leaves zero-length LUT entries that would stall a chain:
         // make them consume one bit, so that the loops below need no guard
@@ -134,19 +149,29 @@ __global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *_
         const uint32_t SW = max(1u, (nw + kOneThreads - 1) / kOneThreads), S = 32u * SW;
         const uint32_t start = (uint32_t)tid * S, limit = min(start + S, nbits);
         const bool active = start < nbits;
+        const int nact = (int)((nbits + S - 1) / S);
         uint32_t b = nbits, e = nbits, cnt = 0;  // first boundary in the sub-sequence, first boundary past it, symbols between
-        if (active) {
-            uint32_t pos = start > kOverlapBits ? start - kOverlapBits : 0u;
-            while (pos < start) pos += lut_at(lutb, sm.sst, pos) & 0xFFu;
-            b = pos;
-            while (pos < limit) { pos += lut_at(lutb, sm.sst, pos) & 0xFFu; ++cnt; }
-            e = pos;
+        uint32_t runin = kOverlapBits;
+        for (int attempt = 0;; ++attempt) {
+            if (active) {
+                uint32_t pos = start > runin ? start - runin : 0u;
+                while (pos < start) pos += lut_at(lutb, sm.sst, pos) & 0xFFu;
+                b = pos;
+                cnt = 0;
+                while (pos < limit) { pos += lut_at(lutb, sm.sst, pos) & 0xFFu; ++cnt; }
+                e = pos;
+            }
+            sm.E[tid] = e;
+            __syncthreads();
+            const uint32_t prev = tid ? sm.E[tid - 1] : 0u;
+            const int broken = __syncthreads_count(active && prev != b);
+            if (4 * broken <= nact || attempt == 1) break;  // (exactly one retry: S can be as small as the first run-in)
+            runin = max(2u * S, 4u * kOverlapBits);  // the code re-synchronises slowly: give every chain room to find its feet
         }
-        sm.E[tid] = e;
-        __syncthreads();
+        FLIC_PHASE(1)  // speculative chains
 
-        // ---- 2. make the chain consistent: b[t] must be e[t-1]
-        for (;;) {
+        // ---- 2. make the chain consistent: b[t] must be e[t-1].  After round r the first r+1 threads are final.
+        for (int round = 0; round < kOneThreads; ++round) {
             const uint32_t prev = tid ? sm.E[tid - 1] : 0u;
             bool changed = false;
             if (active && prev != b) {
@@ -161,6 +186,7 @@ __global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *_
             sm.E[tid] = e;
             if (!__syncthreads_or(changed)) break;
         }
+        FLIC_PHASE(2)  // correction rounds
 
         // ---- 3. first symbol index of every thread
         const uint32_t incl = warp_incl_scan(cnt, lane);
@@ -170,11 +196,12 @@ __global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *_
 #pragma unroll
         for (int k = 0; k < kOneWarps; ++k) { const uint32_t s = sm.wsum[k]; base += k < warp ? s : 0u; total += s; }
         if (total < nsym && tid == 0) atomicOr(err, kErrFormat);  // fewer symbols than the block has (a few more: the padding)
+        FLIC_PHASE(5)  // scan
 
         // ---- 4. the real decode, into the dense residual buffer
         if (cnt && base < nsym) {
             const uint32_t n = min(cnt, nsym - base);
-            uint8_t *dst = sm.res + base;
+            uint8_t *dst = sm.u.res + base;
             uint32_t pos = b;
             for (uint32_t i = 0; i < n; ++i) {
                 const uint32_t en = lut_at(lutb, sm.sst, pos);
@@ -184,6 +211,7 @@ __global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *_
         }
     }
     __syncthreads();
+    FLIC_PHASE(6)  // final decode
 
     // ---- 5. un-prediction and stores
     // coded byte j of a pixel belongs to the j-th channel that is not flat: one PRMT spreads a pixel's CS bytes
@@ -203,7 +231,7 @@ __global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *_
     if (warp == 0) {  // column 0: pixel (r, 0) = sum of the first residuals of rows 0..r
         uint32_t fp = 0;
         if (lane < (int)p.bha) {
-            const uint8_t *t = sm.res + lane * rowsym;
+            const uint8_t *t = sm.u.res + lane * rowsym;
             for (uint32_t j = 0; j < CS; ++j) fp |= (uint32_t)t[j] << (8 * j);
         }
         fp = __byte_perm(fp, 0u, sel);
@@ -219,7 +247,7 @@ __global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *_
     for (int r = warp; r < (int)p.bha; r += kOneWarps) {
         const uint32_t above = r ? sm.vrow[r - 1] : 0u;
         uint32_t w[4] = {0, 0, 0, 0}, px[4];
-        const uint8_t *t = sm.res + r * rowsym + 4 * CS * lane;
+        const uint8_t *t = sm.u.res + r * rowsym + 4 * CS * lane;
         if (npx) {
             if (word_rows) {
                 const uint32_t *t32 = reinterpret_cast<const uint32_t *>(t);
@@ -263,10 +291,12 @@ __global__ void __launch_bounds__(kOneThreads, 5) k_decode_one(const uint32_t *_
             for (int i = 0; i < npx * C; ++i) dst[i] = (uint8_t)(o[i >> 2] >> (8 * (i & 3)));
         }
     }
+    FLIC_PHASE(7)  // un-prediction + stores
+#undef FLIC_PHASE
 }
 
 void launch_decode_one(const uint32_t *d_streams, const unsigned long long *d_offsets, const Geo &g, uint8_t *d_pixels,
-                       uint32_t *d_err, cudaStream_t s) {
+                       uint32_t *d_err, unsigned long long *d_phase_clk, cudaStream_t s) {
     const uint64_t total = (uint64_t)g.n * g.nb;
 #define FLIC_ONE(C)                                                                                                  \
     do {                                                                                                             \
@@ -275,7 +305,7 @@ void launch_decode_one(const uint32_t *d_streams, const unsigned long long *d_of
             cudaFuncSetAttribute(k_decode_one<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OneSmem<C>)); \
             attr = true;                                                                                             \
         }                                                                                                            \
-        k_decode_one<C><<<(unsigned)total, kOneThreads, sizeof(OneSmem<C>), s>>>(d_streams, d_offsets, g, d_pixels, d_err); \
+        k_decode_one<C><<<(unsigned)total, kOneThreads, sizeof(OneSmem<C>), s>>>(d_streams, d_offsets, g, d_pixels, d_err, d_phase_clk); \
     } while (0)
     switch (g.c) {
         case 1: FLIC_ONE(1); break;

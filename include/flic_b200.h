@@ -217,12 +217,14 @@ int flic_stage_tables(flic_ctx *ctx, const uint16_t *d_hist, uint64_t n_blocks_t
 int flic_set_kernel_timing(flic_ctx *ctx, int enable);
 int flic_get_kernel_times(flic_ctx *ctx, double ms[FLIC_K_COUNT], uint64_t counts[FLIC_K_COUNT]);
 
-/* Debug: when the context was created with FLIC_PHASE_CLOCKS=1 in the environment, thread 0 of every k_encode
- * CTA accumulates the SM cycles it spent in each phase of a block (0 ticket+clear, 1 load+residuals+histogram,
- * 2 histogram reduce, 3 code table, 4 pack, 5 look-back, 6 copy-out); this reads and clears the sums.
- * FLIC_E_UNSUPPORTED otherwise (the kernel then carries a null pointer and measures nothing). */
+/* Debug: when the context was created with FLIC_PHASE_CLOCKS=1 in the environment, thread 0 of every CTA of the
+ * two block-pipelined kernels accumulates the SM cycles it spent in each phase of a block; this reads and clears
+ * the sums.  cycles[0..7]: k_encode (0 ticket+clear, 1 load+residuals+histogram, 2 histogram reduce, 3 code table,
+ * 4 pack, 5 look-back, 6 copy-out); cycles[8..15]: k_decode_one (0 stream copy+LUT, 1 speculative chains,
+ * 2 correction rounds, 3 entry-offset table, 4 walk, 5 scan, 6 final decode, 7 un-prediction+stores).
+ * FLIC_E_UNSUPPORTED otherwise (the kernels then carry a null pointer and measure nothing). */
 #define FLIC_PHASES 8
-int flic_get_phase_clocks(flic_ctx *ctx, uint64_t cycles[FLIC_PHASES]);
+int flic_get_phase_clocks(flic_ctx *ctx, uint64_t cycles[2 * FLIC_PHASES]);
 
 /* Number of kernel launches issued through ctx since creation (bench.py's gpu_launches). */
 uint64_t flic_launch_count(const flic_ctx *ctx);

@@ -18,15 +18,27 @@ streams = torch.empty(n * flic.max_stream_bytes(w, h, c), dtype=torch.uint8, dev
 off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
 for _ in range(3):
     codec.encode_batch_device(px, streams, off, flags)
+out = torch.empty_like(px)
 codec.check(); codec.phase_clocks()
 K = 5
 for _ in range(K):
     codec.encode_batch_device(px, streams, off, flags)
+    if flags & 0x20:
+        codec.decode_batch_device(streams, off, out, flags)
 codec.check()
-cyc = codec.phase_clocks()
+cyc_all = codec.phase_clocks()
+cyc = cyc_all[:8]
 nblk = n * (-(-w // 128)) * (-(-h // 32)) * K
 names = ["ticket+clear", "load+resid+hist", "hist reduce", "table", "pack", "look-back", "copy-out", "-"]
 tot = sum(cyc)
 print(wl, hex(flags), "blocks", nblk, "cycles/block", round(tot / nblk))
 for nme, cy in zip(names, cyc):
     print(f"  {nme:18s} {cy / nblk:9.0f} cyc/block  {100 * cy / max(tot, 1):5.1f} %")
+
+if flags & 0x20:
+    cyc = cyc_all[8:]
+    names = ["stream copy + LUT", "speculative chains", "correction rounds", "2b offset table", "2b walk", "scan", "final decode", "un-predict + store"]
+    tot = sum(cyc)
+    print("k_decode_one: cycles/block", round(tot / nblk))
+    for nme, cy in zip(names, cyc):
+        print(f"  {nme:18s} {cy / nblk:9.0f} cyc/block  {100 * cy / max(tot, 1):5.1f} %")
