@@ -290,6 +290,16 @@ static int make_geo(const void *base, uint32_t n, uint32_t w, uint32_t h, uint32
     return FLIC_OK;
 }
 
+static bool make_tile_map(const Geo &g, const uint8_t *d_pixels, CUtensorMapDataType dt, uint32_t elem_bytes, uint32_t box_elems,
+                          CUtensorMapSwizzle swz, CUtensorMap *tm);
+// TMA descriptor for the encoder's pixel tile loads: u32 elements, a box of one whole block (32 rows x 128*C bytes),
+// no swizzle (lanes read 4*C consecutive bytes: conflict-free as it is).  FLIC_NO_TMA=1 turns both TMA paths off.
+static bool make_load_map(const Geo &g, const uint8_t *d_pixels, CUtensorMap *tm) {
+    static const bool off = getenv("FLIC_NO_TMA_LOAD") != nullptr;  // A/B switch for the load path alone
+    if (off) return false;
+    return make_tile_map(g, d_pixels, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, 32u * g.c, CU_TENSOR_MAP_SWIZZLE_NONE, tm);
+}
+
 extern "C" int flic_stage_histograms(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t n, uint32_t w, uint32_t h,
                                      uint32_t c, uint32_t flags, uint16_t *d_hist, uint32_t *d_flat, void *stream) {
     if (!ctx || !d_pixels || !d_hist) return FLIC_E_ARG;
@@ -297,7 +307,10 @@ extern "C" int flic_stage_histograms(flic_ctx *ctx, const uint8_t *d_pixels, uin
     int rc = make_geo(d_pixels, n, w, h, c, flags, &g);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
-    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, (cudaStream_t)stream); launch_histograms(d_pixels, g, d_hist, nullptr, reinterpret_cast<uint2 *>(d_flat), (cudaStream_t)stream); }
+    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, (cudaStream_t)stream);
+      alignas(64) CUtensorMap tm;
+      const bool tma = make_load_map(g, d_pixels, &tm);
+      launch_histograms(d_pixels, g, d_hist, nullptr, reinterpret_cast<uint2 *>(d_flat), tma ? &tm : nullptr, (cudaStream_t)stream); }
     ctx->launches += 1;
     CU(cudaGetLastError());
     return FLIC_OK;
@@ -349,7 +362,10 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
           launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s); }
         ctx->launches += 2;
     } else {
-        { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s); launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, ctx->d_flat, s); }
+        { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s);
+          alignas(64) CUtensorMap tm;
+          const bool tma = make_load_map(g, d_pixels, &tm);
+          launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, ctx->d_flat, tma ? &tm : nullptr, s); }
         { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, (uint64_t)n * g.nb, ctx->d_table, ctx->d_bits, s); }
         bool fused;
         { KernelTimer t(ctx, FLIC_K_SLOTS, s);
@@ -369,10 +385,11 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
     return FLIC_OK;
 }
 
-// TMA descriptor of a tightly packed pixel batch for the decoders' store path: 3-D {row bytes, rows, images},
-// box_bytes x 32 rows boxes.  Returns false when the layout does not qualify (then the kernel stores directly)
-// or the driver entry point is missing.
-static bool make_pixel_map(const Geo &g, uint8_t *d_pixels, uint32_t box_bytes, CUtensorMapSwizzle swz, CUtensorMap *tm) {
+// TMA descriptor of a tightly packed pixel batch: 3-D {row elements, rows, images}, boxes of box_elems x 32 rows.
+// Returns false when the layout does not qualify (then the kernels load / store directly) or the driver entry
+// point is missing.
+static bool make_tile_map(const Geo &g, const uint8_t *d_pixels, CUtensorMapDataType dt, uint32_t elem_bytes, uint32_t box_elems,
+                          CUtensorMapSwizzle swz, CUtensorMap *tm) {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -385,11 +402,11 @@ static bool make_pixel_map(const Geo &g, uint8_t *d_pixels, uint32_t box_bytes, 
         return (encode_fn)fn;
     }();
     static const bool off = getenv("FLIC_NO_TMA") != nullptr;
-    if (off || !encode || !g.aligned16) return false;
-    const cuuint64_t dims[3] = {g.pitch, g.h, g.n};
+    if (off || !encode || !g.aligned16 || box_elems > 256) return false;
+    const cuuint64_t dims[3] = {g.pitch / elem_bytes, g.h, g.n};
     const cuuint64_t strides[2] = {g.pitch, g.img_stride};
-    const cuuint32_t box[3] = {box_bytes, (cuuint32_t)kBH, 1}, estr[3] = {1, 1, 1};
-    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pixels, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint32_t box[3] = {box_elems, (cuuint32_t)kBH, 1}, estr[3] = {1, 1, 1};
+    return encode(tm, dt, 3, const_cast<uint8_t *>(d_pixels), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -408,7 +425,7 @@ extern "C" int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams,
     } else {
         KernelTimer t(ctx, FLIC_K_DECODE, (cudaStream_t)stream);
         alignas(64) CUtensorMap tm;
-        const bool tma = g.c == 4 && make_pixel_map(g, d_pixels, 64, CU_TENSOR_MAP_SWIZZLE_64B, &tm);
+        const bool tma = g.c == 4 && make_tile_map(g, d_pixels, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 64, CU_TENSOR_MAP_SWIZZLE_64B, &tm);
         launch_decode((const uint32_t *)d_streams, (const unsigned long long *)d_offsets, g, d_pixels, ctx->d_err + 1,
                       tma ? &tm : nullptr, (cudaStream_t)stream);
     }

@@ -183,8 +183,9 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 // launchers (defined in the .cu files, used by api.cu)
+// tensor_map: a CUtensorMap for the TMA tile loads (api.cu: make_load_map), or nullptr for direct loads
 void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, uint2 *d_flat,
-                       cudaStream_t s);
+                       const void *tensor_map, cudaStream_t s);
 void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s);
 void launch_tables_cta(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s);
 int slots_max_resident_ctas();  // how many k_slots CTAs this device keeps resident at once (occupancy API)

@@ -18,6 +18,10 @@
 //
 // Format: DESIGN.md §FLP0 (provisional; not the reference's bitstream —
 // LICENSING.md).  Byte-exact CPU model: oracle/flp0_oracle.c (tests only).
+#include <cstring>
+
+#include <cuda.h>  // CUtensorMap (type only; the driver entry point is resolved in api.cu)
+
 #include "common.cuh"
 
 namespace flic {
@@ -47,15 +51,32 @@ __device__ __forceinline__ uint32_t word_channel_bits(uint32_t mask, int j) {
 // flat (optional): per block {mask of flat channels, their values} (FLP0 §2b).  A channel is flat when all
 // its residuals are zero except the block's first pixel's, i.e. the OR of the others is zero; the histogram
 // then leaves the channel out (bwa*bha - 1 zeros and the first pixel's value are taken back off).
-template <int C, bool SG>
-__global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__restrict__ pixels, Geo g,
+//
+// kTma: the block's pixels (32 rows x 128*C bytes) arrive as ONE TMA tile load (cp.async.bulk.tensor, 3-D map
+// {row words, rows, images} of u32 elements, completion on an mbarrier) issued by one thread while the others
+// clear the sub-histograms; lanes then take their 4*C bytes from shared memory.  Tiles that hang over the image's
+// right or bottom edge are zero-filled by the TMA unit, which is exactly what the direct path's edge handling
+// produces, and the pixel above a row's first pixel is in the tile too.  Needs a 16-byte-aligned batch.
+template <int C, bool SG, bool kTma>
+__global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__restrict__ pixels, Geo g,
                                                             uint16_t *__restrict__ hist, uint32_t *__restrict__ resid,
-                                                            uint2 *__restrict__ flat) {
+                                                            uint2 *__restrict__ flat, const __grid_constant__ CUtensorMap tmap) {
     __shared__ __align__(16) uint32_t sh[kEncWarps][256];
+    __shared__ __align__(128) uint32_t ptile[kTma ? kBH * 32 * C : 4];
+    __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t s_or[C], s_first;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t gb = blockIdx.x;
     const BlockPos p = block_pos(g, gb);
+    if (kTma && tid == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar), dst = (uint32_t)__cvta_generic_to_shared(ptile);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(kBH * 128 * C)) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"((int)(p.x0 * C / 4)), "r"((int)p.y0), "r"((int)p.img), "r"(bar)
+                     : "memory");
+    }
 
     {
         uint4 *z = reinterpret_cast<uint4 *>(&sh[0][0]);
@@ -63,6 +84,17 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
         for (int i = 0; i < kEncWarps * 256 / 4 / kEncThreads; ++i) z[tid + i * kEncThreads] = make_uint4(0, 0, 0, 0);
     }
     if (tid < C) s_or[tid] = 0;
+    if (kTma) {
+        __syncthreads();  // the barrier's initialisation is visible to every thread before anyone waits on it
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar);
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t"
+            "@P1 bra DONE_%=;\n\t"
+            "bra WAIT_%=;\n\t"
+            "DONE_%=:\n\t}" ::"r"(bar) : "memory");
+    }
 
     uint32_t res[kBH / kEncWarps][C];
     uint32_t orw[C];
@@ -79,8 +111,26 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
         for (int j = 0; j < C; ++j) res[q][j] = 0;
         if (r < (int)p.bha) {  // warp-uniform
             uint32_t v[C];
-            load_lane_pixels<C>(row, lane, (int)p.bwa, fast, v, &nv[q]);
-            const uint32_t up = (lane == 0 && r > 0) ? up_pixel<C, SG>(row, g.pitch, fast) : 0u;
+            uint32_t up = 0u;
+            if (kTma) {
+                const uint32_t *t = ptile + (r * 32 + lane) * C;
+                if (C == 4) {
+                    const uint4 x = *reinterpret_cast<const uint4 *>(t);
+                    v[0] = x.x; v[1 % C] = x.y; v[2 % C] = x.z; v[3 % C] = x.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < C; ++j) v[j] = t[j];
+                }
+                nv[q] = C * max(0, min(4, (int)p.bwa - 4 * lane));
+                if (lane == 0 && r > 0) {  // the pixel above this row's first pixel, transformed like the others
+                    up = ptile[(r - 1) * 32 * C];
+                    if (C < 4) up &= (1u << (8 * (C & 3))) - 1u;
+                    if (SG && C >= 3) { const uint32_t gg = (up >> 8) & 0xFFu; up = __vsub4(up, gg | (gg << 16)); }
+                }
+            } else {
+                load_lane_pixels<C>(row, lane, (int)p.bwa, fast, v, &nv[q]);
+                if (lane == 0 && r > 0) up = up_pixel<C, SG>(row, g.pitch, fast);
+            }
             lane_residuals<C, SG>(v, up, lane, res[q]);
 #pragma unroll
             for (int j = 0; j < C; ++j) {
@@ -168,11 +218,17 @@ __global__ void __launch_bounds__(kEncThreads) k_histograms(const uint8_t *__res
 }
 
 void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, uint2 *d_flat,
-                       cudaStream_t s) {
+                       const void *tensor_map, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) && g.c >= 3;
     const unsigned grid = (unsigned)total;
-#define FLIC_HIST(C, SG) k_histograms<C, SG><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid, d_flat)
+    CUtensorMap tm;
+    if (tensor_map) memcpy(&tm, tensor_map, sizeof tm); else memset(&tm, 0, sizeof tm);
+#define FLIC_HIST(C, SG)                                                                                            \
+    do {                                                                                                            \
+        if (tensor_map) k_histograms<C, SG, true><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid, d_flat, tm);  \
+        else k_histograms<C, SG, false><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid, d_flat, tm);            \
+    } while (0)
     switch (g.c) {
         case 1: FLIC_HIST(1, false); break;
         case 2: FLIC_HIST(2, false); break;
