@@ -425,7 +425,10 @@ extern "C" int flic_decode_batch_device(flic_ctx *ctx, const uint8_t *d_streams,
     } else {
         KernelTimer t(ctx, FLIC_K_DECODE, (cudaStream_t)stream);
         alignas(64) CUtensorMap tm;
-        const bool tma = g.c == 4 && make_tile_map(g, d_pixels, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 64, CU_TENSOR_MAP_SWIZZLE_64B, &tm);
+        // TMA tile stores: RGBA in 64-byte rows with the 64 B swizzle, RGB in 96-byte rows (FLIC_NO_TMA_RGB=1: A/B switch)
+        static const bool no_rgb = getenv("FLIC_NO_TMA_RGB") != nullptr;
+        const bool tma = (g.c == 4 && make_tile_map(g, d_pixels, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 64, CU_TENSOR_MAP_SWIZZLE_64B, &tm)) ||
+                         (g.c == 3 && !no_rgb && make_tile_map(g, d_pixels, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 96, CU_TENSOR_MAP_SWIZZLE_NONE, &tm));
         launch_decode((const uint32_t *)d_streams, (const unsigned long long *)d_offsets, g, d_pixels, ctx->d_err + 1,
                       tma ? &tm : nullptr, (cudaStream_t)stream);
     }

@@ -211,7 +211,13 @@ __device__ __forceinline__ void acc_set(Acc &v, int ch, uint32_t val) {
 // r sits at chunk c ^ ((r >> 1) & 3).  Register budget: the loop only carries the tile's shared address
 // (0 = path off); the tile's origin and the descriptor address sit in a record right behind the tile and
 // are read by lane 0 per flush.
-constexpr uint32_t kTileBytes = 2048, kTileStride = kTileBytes + 512;  // 512 B keeps the swizzle phase of the next tile
+// RGB rows go the same way with 96-byte tile rows (two chunks of 16 pixels) and no swizzle: a lane's 16 B stores at a
+// 96-byte pitch are 2-way bank-conflicted, still four times fewer wavefronts than stores straight to global memory.
+// kTma selects the variant at compile time: 0 none, 4 RGBA, 3 RGB (each kernel carries only its own staging).
+template <int kTma> struct TileGeo {
+    static constexpr uint32_t kBytes = kTma == 3 ? 32u * 96u : 32u * 64u;
+    static constexpr uint32_t kStride = kBytes + 512;  // 512 B for the record; keeps the swizzle phase of the next tile
+};
 struct TileRec { unsigned long long map; uint32_t x0b, y0, img, pad; };
 __device__ __forceinline__ void tile_put(uint32_t tile, int lane, int half, const uint32_t *o) {
     const uint32_t row = tile + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
@@ -224,15 +230,23 @@ __device__ __forceinline__ void tile_put(uint32_t tile, int lane, int half, cons
 }
 // amask: the warp's lanes that own a real row (lanes of a ragged bottom block's missing rows have
 // left decode_rows, so a full-mask barrier here would name exited lanes).  Lane 0 always owns a row.
+__device__ __forceinline__ void tile_put3(uint32_t tile, int lane, int half, const uint32_t *o) {  // RGB: 48 B per chunk
+    const uint32_t a = tile + (uint32_t)lane * 96u + (uint32_t)half * 48u;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a + 16u * c), "r"(o[4 * c]), "r"(o[4 * c + 1]), "r"(o[4 * c + 2]),
+                     "r"(o[4 * c + 3]) : "memory");
+}
+template <uint32_t kRecAt>
 __device__ __forceinline__ void tile_flush(uint32_t tile, int lane, uint32_t xbyte, uint32_t amask) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
     __syncwarp(amask);
     if (lane == 0) {
         unsigned long long map;
         uint32_t x0b, y0, img;
-        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(map) : "r"(tile + kTileBytes));
-        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x0b), "=r"(y0) : "r"(tile + kTileBytes + 8));
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(img) : "r"(tile + kTileBytes + 16));
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(map) : "r"(tile + kRecAt));
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x0b), "=r"(y0) : "r"(tile + kRecAt + 8));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(img) : "r"(tile + kRecAt + 16));
         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
                      "r"(x0b + xbyte), "r"(y0), "r"(img), "r"(tile) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -243,7 +257,7 @@ __device__ __forceinline__ void tile_wait(int lane, uint32_t amask) {  // the ti
     __syncwarp(amask);
 }
 
-template <int C, bool SG, int FM, bool kTma>
+template <int C, bool SG, int FM, int kTma>
 __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel, uint32_t m2048, uint8_t *dst, int bwa,
                             bool active, int aligned, int lane, uint32_t fmask, uint32_t fvals, uint32_t pfx,
                             uint32_t tma /* the warp's tile, or 0 */) {
@@ -301,10 +315,13 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
             else
                 decode_chunk<C, SG, FMC, false>(br, rs, acc, luts, wsel, m2048, o);
             uint8_t *d = dst + (size_t)x * C;
-            const int half = (x >> 3) & 1;
-            if (kTma && C == 4 && tma && (half == 1 || x + 2 * U <= bwa)) {  // chunk pairs go out as one TMA tile
+            const int half = (x / U) & 1;
+            if (kTma == 4 && C == 4 && tma && (half == 1 || x + 2 * U <= bwa)) {  // chunk pairs go out as one TMA tile
                 if (half == 0) { if (x > 0) tile_wait(lane, amask); tile_put(tma, lane, 0, o); }
-                else { tile_put(tma, lane, 1, o); tile_flush(tma, lane, (uint32_t)(x - U) * 4u, amask); }
+                else { tile_put(tma, lane, 1, o); tile_flush<TileGeo<4>::kBytes>(tma, lane, (uint32_t)(x - U) * 4u, amask); }
+            } else if (kTma == 3 && C == 3 && tma && (half == 1 || x + 2 * U <= bwa)) {
+                if (half == 0) { if (x > 0) tile_wait(lane, amask); tile_put3(tma, lane, 0, o); }
+                else { tile_put3(tma, lane, 1, o); tile_flush<TileGeo<3>::kBytes>(tma, lane, (uint32_t)(x - U) * 3u, amask); }
             } else if (W == 8 && aligned == 2) {  // one 256-bit store: a whole 32-byte sector per lane and half the LSU wavefronts
                 asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]),
                              "r"(o[3]), "r"(o[4 % W]), "r"(o[5 % W]), "r"(o[6 % W]), "r"(o[7 % W])
@@ -319,7 +336,7 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
             }
         }
     }
-    if (kTma && C == 4 && tma && FM >= 0) tile_wait(lane, amask);  // the tile must outlive the TMA unit's read of it
+    if (kTma == C && tma && FM >= 0) tile_wait(lane, amask);  // the tile must outlive the TMA unit's read of it
     // ragged right edge of the image, and whole rows of blocks with an uncommon flat mask
     for (; x < bwa; ++x) {
 #pragma unroll
@@ -335,12 +352,12 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
 
 // kTma: the RGBA TMA-store variant; the plain variant carries none of that code (its other paths were
 // measurably slower with it compiled in).
-template <bool kTma>
-__global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *__restrict__ streams,
+template <int kTma>
+__global__ void __launch_bounds__(kDecWarps * 32, kTma == 3 ? 8 : 10) k_decode(const uint32_t *__restrict__ streams,
                                                           const unsigned long long *__restrict__ offsets, Geo g,
                                                           uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048, uint32_t pf, uint32_t pf2,
                                                           const __grid_constant__ CUtensorMap tmap) {
-    __shared__ __align__(1024) uint8_t tiles[kTma ? kDecWarps : 1][kTma ? kTileStride : 16];  // TMA store staging, 32 rows x 64 B per warp (+ record)
+    __shared__ __align__(1024) uint8_t tiles[kTma ? kDecWarps : 1][kTma ? TileGeo<kTma>::kStride : 16];  // TMA store staging, 32 rows x 64 / 96 B per warp (+ record)
     __shared__ __align__(16) uint16_t luts[kDecWarps][kLutSize];
     __shared__ LutScratch scratch[kDecWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -400,12 +417,12 @@ __global__ void __launch_bounds__(kDecWarps * 32, 10) k_decode(const uint32_t *_
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) != 0 && g.c >= 3;
     const int aligned = g.aligned16 ? (g.aligned32 ? 2 : 1) : 0;  // 0: byte stores, 1: 16-byte, 2: 32-byte
     uint32_t tp = 0;
-    if (kTma && g.c == 4) {
+    if (kTma && (int)g.c == kTma) {
         tp = (uint32_t)__cvta_generic_to_shared(&tiles[warp][0]);
         if (lane == 0) {
-            TileRec *rec = reinterpret_cast<TileRec *>(&tiles[warp][kTileBytes]);
+            TileRec *rec = reinterpret_cast<TileRec *>(&tiles[warp][kTma ? TileGeo<kTma>::kBytes : 0]);
             rec->map = reinterpret_cast<unsigned long long>(&tmap);
-            rec->x0b = p.x0 * 4u; rec->y0 = p.y0; rec->img = p.img;
+            rec->x0b = p.x0 * g.c; rec->y0 = p.y0; rec->img = p.img;
         }
         __syncwarp();
     }
@@ -440,9 +457,11 @@ void launch_decode(const uint32_t *d_streams, const unsigned long long *d_offset
     CUtensorMap tm;
     if (tensor_map) memcpy(&tm, tensor_map, sizeof tm); else memset(&tm, 0, sizeof tm);
     if (tensor_map && g.c == 4)
-        k_decode<true><<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words, tm);
+        k_decode<4><<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words, tm);
+    else if (tensor_map && g.c == 3)
+        k_decode<3><<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words, tm);
     else
-        k_decode<false><<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words, tm);
+        k_decode<0><<<grid, kDecWarps * 32, 0, s>>>(d_streams, d_offsets, g, d_pixels, d_err, 2048u, kPrefetchChunks, kPrefetchL2Words, tm);
 }
 
 }  // namespace flic

@@ -18,6 +18,7 @@
 //
 // Format: DESIGN.md §FLP0 (provisional; not the reference's bitstream —
 // LICENSING.md).  Byte-exact CPU model: oracle/flp0_oracle.c (tests only).
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda.h>  // CUtensorMap (type only; the driver entry point is resolved in api.cu)
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__
                 orw[j] |= x;
             }
         }
-        if (resid) {
+        if (resid && !kTma) {
             uint32_t *t = resid + ((gb * kBH + r) * 32 + lane) * C;
             if (C == 4) *reinterpret_cast<uint4 *>(t) = make_uint4(res[q][0], res[q][1 % C], res[q][2 % C], res[q][3 % C]);
             else if (C == 2) *reinterpret_cast<uint2 *>(t) = make_uint2(res[q][0], res[q][1 % C]);
@@ -155,6 +156,20 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__
         row += kEncWarps * g.pitch;
     }
     __syncthreads();
+    if (kTma && resid) {
+        // every read of the pixel tile is done: the residuals take its place (same layout as the residual plane's
+        // tile of this block) and leave as ONE bulk store instead of four 128-bit stores per thread
+#pragma unroll
+        for (int q = 0; q < kBH / kEncWarps; ++q) {
+            uint32_t *t = ptile + ((warp + kEncWarps * q) * 32 + lane) * C;
+            if (C == 4) *reinterpret_cast<uint4 *>(t) = make_uint4(res[q][0], res[q][1 % C], res[q][2 % C], res[q][3 % C]);
+            else {
+#pragma unroll
+                for (int j = 0; j < C; ++j) t[j] = res[q][j];
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+    }
     {   // bytes past the lane's last real pixel hold garbage differences: keep them out of the OR
         const int nvl = C * max(0, min(4, (int)p.bwa - 4 * lane));
         constexpr int NA = C == 4 ? 1 : C;  // RGBA: byte b is channel b in every word, one accumulator does
@@ -194,6 +209,11 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__
     }
     if (C == 4 && lane == 0 && zero_rows) atomicAdd(&sh[warp][0], zero_rows * (uint32_t)kBW);
     __syncthreads();
+    if (kTma && resid && tid == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(resid + gb * (uint64_t)(kBH * 32 * C)),
+                     "r"((uint32_t)__cvta_generic_to_shared(ptile)), "r"((uint32_t)(kBH * 128 * C)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < kEncWarps; ++k) s += sh[k][tid];
@@ -215,6 +235,7 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__
         if (flat && tid == 0) flat[gb] = make_uint2((flatb * 0x01020408u) >> 24, first & (flatb * 0xFFu));
     }
     hist[gb * 256 + tid] = (uint16_t)s;
+    if (kTma && resid && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must outlive the store's read of it
 }
 
 void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, uint32_t *d_resid, uint2 *d_flat,
@@ -245,10 +266,11 @@ void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, 
 // (an internal node is taken only if strictly lighter than the next leaf) is FLP0 §3.2's.
 constexpr int kTabPitch = 258;  // u16 elements per row: 129 words
 constexpr int kTabBpw = 8;      // blocks per warp: 7.7 KB of smem per warp -> ~29 warps per SM
-struct TabSmem {
+template <int BPW>
+struct TabSmemT {
     uint32_t key[256];      // (count << 8) | symbol of the block being sorted
-    uint16_t A[kTabBpw * kTabPitch];  // merge arrays, one row per lane-owned block; odd word pitch = conflict-free in step
-    uint8_t ord[kTabBpw][256];   // sorted symbol order per block
+    uint16_t A[BPW * kTabPitch];  // merge arrays, one row per lane-owned block; odd word pitch = conflict-free in step
+    uint8_t ord[BPW][256];   // sorted symbol order per block
     uint8_t lenS[256];      // code length per SYMBOL of the block being finished
     uint8_t lenR[256];      // code length per sorted RANK
     uint32_t next[16];      // first canonical code per length
@@ -367,9 +389,10 @@ __device__ __forceinline__ void sort_block(uint32_t *key, int n, uint16_t *Arow,
 
 // bits (optional): per block, the sum over symbols of count x code length — with the geometry that is
 // the block's slot size (FLP0 §7), so every block's output position is known before k_pack runs.
+template <int BPW>
 __global__ void __launch_bounds__(32) k_tables(const uint16_t *__restrict__ hist, uint64_t nblocks,
                                                uint16_t *__restrict__ table, uint32_t *__restrict__ bits, int bpw) {
-    __shared__ __align__(16) TabSmem s;
+    __shared__ __align__(16) TabSmemT<BPW> s;
     const int lane = threadIdx.x;
     const uint64_t first = (uint64_t)blockIdx.x * bpw;
     const int cnt = (int)min((uint64_t)bpw, nblocks - first);
@@ -475,11 +498,15 @@ __global__ void __launch_bounds__(32) k_tables(const uint16_t *__restrict__ hist
 
 void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s) {
     // one block per warp for small jobs (latency: 512x512 RGB 27 -> 21 us), a few when that still fills the
-    // chip, kTabBpw (merge lanes busy) for large jobs
+    // chip, up to `cap` blocks per warp (merge lanes busy) for large jobs.  FLIC_TAB_BPW: experiment switch.
+    static const int cap = [] { const char *e = getenv("FLIC_TAB_BPW"); const int v = e ? atoi(e) : kTabBpw; return v == 2 || v == 4 || v == 16 ? v : kTabBpw; }();
     uint64_t want = nblocks / (148ull * 16);
-    int bpw = (int)(want < 1 ? 1 : (want > kTabBpw ? kTabBpw : want));
+    int bpw = (int)(want < 1 ? 1 : (want > (uint64_t)cap ? cap : want));
     unsigned grid = (unsigned)((nblocks + bpw - 1) / bpw);
-    k_tables<<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
+    if (cap == 2) k_tables<2><<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
+    else if (cap == 4) k_tables<4><<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
+    else if (cap == 16) k_tables<16><<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
+    else k_tables<kTabBpw><<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
 }
 
 // ------------------------------------------------------------------ k_finalize
