@@ -392,7 +392,7 @@ def e2e_pipelined(D, codec, host_px, cap, n, flags, steps):
 
     run(2)
     assert np.array_equal(h_out, h_in), "host round trip is not lossless"
-    k = max(3, min(steps, 6))
+    k = max(3, min(steps, 10))
     D.barrier()
     t0 = time.perf_counter()
     nbytes = run(k)

@@ -23,14 +23,23 @@ namespace {
 // streams with double-buffered device buffers, so PCIe in, compute and PCIe out overlap.  Encode and decode
 // own separate pipes, so an encode call and a decode call (flic_*_submit) can be in flight together and use
 // both directions of the link at once.
-// kDepth chunks are in flight per direction.  The copy engines are FIFOs shared by everything on the device, so a
-// copy that is enqueued before its inputs are ready (a stream-wait on a kernel's event in front of it) stalls every
-// copy behind it — including the other call's when an encode and a decode are in flight together (measured: both
-// calls together took exactly the sum of the two alone, while the bare link carries both patterns at once in 0.8 of
-// that).  Hence the rule in both pipelines below: A COPY IS ISSUED ONLY WHEN IT CAN START — the host has already
-// seen the event it depends on — and stream sizes come back through mapped pinned memory the kernels write to,
-// not through a device-to-host copy queued behind the kernels.
+// Up to kDepth chunks are in flight per call.  How many actually are is decided chunk by chunk (measured on a B200
+// box, 64 x 4K RGBA: tools/e2e_probe.py, profiles/r02_link_probe.txt):
+//   * a call that has the link to itself wants a deep pipeline: 42 ms at depth >= 3 against 57 ms at depth 1;
+//   * an encode and a decode in flight TOGETHER want depth 1: 68.5 ms for both (the bare link does the same copy
+//     pattern in 67.6 ms), against 86 ms at any depth >= 2 — exactly the sum of the two calls alone.  With more than
+//     one copy per call queued, the copy engines serve the two calls' same-direction copies in convoys and the
+//     opposite direction idles.
+// So the lookahead is kDepth while the other direction's pipe is idle and 1 while it is active.  Two more rules, from
+// the same measurements: a copy is issued only when it can start (the host has already seen the event it depends
+// on), and the encoder's stream sizes come back through mapped pinned memory the kernels write to, not through a
+// device-to-host copy queued behind the kernels.
 constexpr int kDepth = 4;
+// deepest lookahead a call may use (FLIC_PIPE_DEPTH: experiment switch, 1..kDepth)
+static int pipe_depth() {
+    static const int d = [] { const char *e = getenv("FLIC_PIPE_DEPTH"); const int v = e ? atoi(e) : kDepth; return v < 1 ? 1 : (v > kDepth ? kDepth : v); }();
+    return d;
+}
 struct Pipe {
     uint8_t *d_pix[kDepth] = {}, *d_str[kDepth] = {};
     unsigned long long *d_off[kDepth] = {};
@@ -39,6 +48,7 @@ struct Pipe {
     uint64_t pix_cap = 0, str_cap = 0, off_cap = 0;
     cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;  // kernels / H2D / D2H
     cudaEvent_t ev_in[kDepth] = {}, ev_k[kDepth] = {}, ev_out[kDepth] = {};
+    std::atomic<int> active{0};  // a call is running through this pipe (the other pipe throttles its lookahead)
     // submit/wait
     std::thread worker;
     bool busy = false;
@@ -618,7 +628,7 @@ static int encode_batch_impl(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n,
     //   B  kernels (their wait for the H2D is on the compute queue, where it stalls nobody else); the stream
     //      offsets land in mapped pinned memory
     //   C  wait for the kernels, place the chunk in the caller's buffer, D2H of exactly that many bytes
-    uint32_t issued_in = 0;
+    uint32_t issued_in = 0, launched = 0, retired = 0;
     auto stage_a = [&]() -> int {
         const uint32_t k = issued_in++;
         const int b = k % kDepth;
@@ -650,14 +660,15 @@ static int encode_batch_impl(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n,
         out_pos += total;
         return FLIC_OK;
     };
-    while (rc == FLIC_OK && issued_in < chunks && issued_in < (uint32_t)kDepth) rc = stage_a();  // every staging buffer is free
-    for (uint32_t step = 0; step <= chunks && rc == FLIC_OK; ++step) {
-        if (step < chunks) rc = stage_b(step);
-        if (rc == FLIC_OK && step >= 1) {
-            rc = stage_c(step - 1);
-            if (rc == FLIC_OK && issued_in < chunks) rc = stage_a();  // the kernels of chunk step-1 are done: its pixel buffer is free
-        }
+    Pipe &other = ctx->dec;
+    P.active.store(1);
+    while (rc == FLIC_OK && retired < chunks) {
+        const uint32_t lim = other.active.load() ? 1u : (uint32_t)pipe_depth();
+        while (rc == FLIC_OK && issued_in < chunks && issued_in - retired < lim) rc = stage_a();  // the buffers of retired chunks are free
+        while (rc == FLIC_OK && launched < issued_in) rc = stage_b(launched++);
+        if (rc == FLIC_OK) rc = stage_c(retired++);
     }
+    P.active.store(0);
     drain(P);  // success or not: nothing may touch the caller's buffers after the call returns
     const int chk = check_word(ctx, 0, P.s_k);
     return rc ? rc : chk;
@@ -742,12 +753,15 @@ static int decode_run(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h
         CU(cudaEventRecord(P.ev_out[b], P.s_out));
         return FLIC_OK;
     };
-    uint32_t issued = 0;
-    while (rc == FLIC_OK && issued < chunks && issued < (uint32_t)kDepth) rc = issue(issued++);
-    for (uint32_t k = 0; k < chunks && rc == FLIC_OK; ++k) {
-        rc = retire(k);
-        if (rc == FLIC_OK && issued < chunks) rc = issue(issued++);
+    Pipe &other = ctx->enc;
+    uint32_t issued = 0, retired = 0;
+    P.active.store(1);
+    while (rc == FLIC_OK && retired < chunks) {
+        const uint32_t lim = other.active.load() ? 1u : (uint32_t)pipe_depth();
+        while (rc == FLIC_OK && issued < chunks && issued - retired < lim) rc = issue(issued++);
+        if (rc == FLIC_OK) rc = retire(retired++);
     }
+    P.active.store(0);
     drain(P);
     return rc;
 }
