@@ -40,6 +40,23 @@ static int pipe_depth() {
     static const int d = [] { const char *e = getenv("FLIC_PIPE_DEPTH"); const int v = e ? atoi(e) : kDepth; return v < 1 ? 1 : (v > kDepth ? kDepth : v); }();
     return d;
 }
+// lookahead while the other direction's call is in flight (FLIC_PIPE_BOTH_DEPTH: experiment switch)
+static int pipe_depth_both() {
+    static const int d = [] { const char *e = getenv("FLIC_PIPE_BOTH_DEPTH"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > kDepth ? kDepth : v); }();
+    return d;
+}
+// Host wait for a chunk's kernels.  At depth 1 the wait is on the critical path of every chunk, so it polls (a blocking
+// wait costs a sleep/wake-up per chunk); with a deep pipeline it blocks, leaving the cores to the other ranks' workers.
+static cudaError_t wait_chunk(cudaEvent_t ev, bool poll) {
+    static const int mode = [] { const char *e = getenv("FLIC_WAIT"); return e ? (strcmp(e, "poll") == 0 ? 1 : (strcmp(e, "block") == 0 ? 2 : 0)) : 0; }();
+    if (mode == 1) poll = true;
+    if (mode == 2) poll = false;
+    if (!poll) return cudaEventSynchronize(ev);
+    for (;;) {
+        const cudaError_t e = cudaEventQuery(ev);
+        if (e != cudaErrorNotReady) return e;
+    }
+}
 struct Pipe {
     uint8_t *d_pix[kDepth] = {}, *d_str[kDepth] = {};
     unsigned long long *d_off[kDepth] = {};
@@ -650,7 +667,7 @@ static int encode_batch_impl(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n,
     auto stage_c = [&](uint32_t k) -> int {
         const int b = k % kDepth;
         const uint32_t first = k * m, cnt = (first + m <= n) ? m : n - first;
-        CU(cudaEventSynchronize(P.ev_k[b]));
+        CU(wait_chunk(P.ev_k[b], issued_in - k <= 1));
         const uint64_t total = P.h_off[b][cnt];
         if (total > cnt * img_worst) return FLIC_E_INTERNAL;  // kernels flagged a capacity overrun
         if (out_pos + total > capacity_bytes) return FLIC_E_CAPACITY;
@@ -663,7 +680,7 @@ static int encode_batch_impl(flic_ctx *ctx, const uint8_t *h_pixels, uint32_t n,
     Pipe &other = ctx->dec;
     P.active.store(1);
     while (rc == FLIC_OK && retired < chunks) {
-        const uint32_t lim = other.active.load() ? 1u : (uint32_t)pipe_depth();
+        const uint32_t lim = other.active.load() ? (uint32_t)pipe_depth_both() : (uint32_t)pipe_depth();
         while (rc == FLIC_OK && issued_in < chunks && issued_in - retired < lim) rc = stage_a();  // the buffers of retired chunks are free
         while (rc == FLIC_OK && launched < issued_in) rc = stage_b(launched++);
         if (rc == FLIC_OK) rc = stage_c(retired++);
@@ -729,6 +746,7 @@ static int decode_run(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h
     if (rc) return rc;
     // Same rule as the encoder's pipeline: the H2D of a chunk is issued when the host has seen the kernel that last
     // read the staging buffer finish; the D2H of a chunk is issued when the host has seen its kernel finish.
+    uint32_t issued = 0, retired = 0;
     auto issue = [&](uint32_t k) -> int {
         const int b = k % kDepth;
         const uint32_t f0 = lo + k * m, cnt = (f0 + m <= hi) ? m : hi - f0;
@@ -748,16 +766,15 @@ static int decode_run(flic_ctx *ctx, const uint8_t *h_streams, const uint64_t *h
     auto retire = [&](uint32_t k) -> int {
         const int b = k % kDepth;
         const uint32_t f0 = lo + k * m, cnt = (f0 + m <= hi) ? m : hi - f0;
-        CU(cudaEventSynchronize(P.ev_k[b]));  // the chunk's pixels exist: its D2H is runnable, its stream buffer is free
+        CU(wait_chunk(P.ev_k[b], issued - k <= 1));  // the chunk's pixels exist: its D2H is runnable, its stream buffer is free
         CU(cudaMemcpyAsync(h_pixels + (uint64_t)(f0 - lo) * img_bytes, P.d_pix[b], cnt * img_bytes, cudaMemcpyDeviceToHost, P.s_out));
         CU(cudaEventRecord(P.ev_out[b], P.s_out));
         return FLIC_OK;
     };
     Pipe &other = ctx->enc;
-    uint32_t issued = 0, retired = 0;
     P.active.store(1);
     while (rc == FLIC_OK && retired < chunks) {
-        const uint32_t lim = other.active.load() ? 1u : (uint32_t)pipe_depth();
+        const uint32_t lim = other.active.load() ? (uint32_t)pipe_depth_both() : (uint32_t)pipe_depth();
         while (rc == FLIC_OK && issued < chunks && issued - retired < lim) rc = issue(issued++);
         if (rc == FLIC_OK) rc = retire(retired++);
     }
