@@ -122,3 +122,57 @@ def test_splice_rejects_misaligned_parts(flic, oracle):
     assert e.value.code == -1
     with pytest.raises(flic.FlicError):       # widths differ
         flic.splice_block_rows([oracle.encode(img[:64]), oracle.encode(img[64:, :100])])
+
+
+@pytest.mark.parametrize("flags", [0x21, 0x41, 0x31, 0x51])
+def test_layout_flags_peek_and_splice(flic, oracle, flags):
+    """The two optional layouts (one bit stream per block; exact block sizes) are header flags: peek reports them,
+    the combination is refused, and block-row parts splice into the full stream in either layout (host code)."""
+    img = cases.gradient(300, 100, 3, 33)
+    full = oracle.encode(img, flags)
+    assert flic.peek(full)["flags"] == flags
+    parts = [oracle.encode(img[:64], flags), oracle.encode(img[64:], flags)]
+    assert np.array_equal(flic.splice_block_rows(parts), full)
+    bad = full.copy(); bad[7] = 0x61      # ONE_STREAM | EXACT
+    with pytest.raises(flic.FlicError) as e:
+        flic.peek(bad)
+    assert e.value.code == -3
+    bad[7] = 0x81                           # reserved bit
+    with pytest.raises(flic.FlicError):
+        flic.peek(bad)
+    with pytest.raises(flic.FlicError):     # parts of different layouts do not splice
+        flic.splice_block_rows([oracle.encode(img[:64], flags), oracle.encode(img[64:], 0x01)])
+
+
+def test_splice_plan(flic, oracle):
+    """flic_splice_plan: where every part's directory entries and payload land in the spliced stream (what the ranks
+    of the multi-GPU path address their sends with) — checked against an actual host splice."""
+    img = cases.gradient(260, 200, 4, 34)
+    cuts = [(0, 64), (64, 160), (160, 200)]
+    parts = [oracle.encode(img[a:b]) for a, b in cuts]
+    infos = [flic.peek(p) for p in parts]
+    nbs, pws = [i["n_blocks"] for i in infos], [i["payload_words"] for i in infos]
+    doff, poff, total = flic.splice_plan(nbs, pws)
+    full = flic.splice_block_rows(parts)
+    assert total == full.size
+    base = 0
+    for p, nb, pw, do, po in zip(parts, nbs, pws, doff, poff):
+        d_part = np.frombuffer(p[32: 32 + 4 * nb].tobytes(), np.uint32)
+        d_full = np.frombuffer(full[do: do + 4 * nb].tobytes(), np.uint32)
+        assert np.array_equal(d_full, d_part + np.uint32(base))                          # rebased directory segment
+        assert np.array_equal(full[po: po + 4 * pw], p[32 + 4 * (nb + 1): 32 + 4 * (nb + 1) + 4 * pw])  # payload in place
+        base += pw
+    lib = flic.load_library()
+    import ctypes as C
+    assert lib.flic_splice_plan(None, None, 0, None, None, None) == -1
+
+
+def test_host_only_argument_checks(flic):
+    """Entry points that can refuse without a device do so with FLIC_E_ARG, never a crash."""
+    lib = flic.load_library()
+    assert lib.flic_set_option(None, 1, 0) == -1
+    assert lib.flic_wait(None, 0) == -1
+    assert lib.flic_host_register(None, 0) == -1
+    assert lib.flic_encode_submit(None, None, 0, 0, 0, 0, 0, None, 0, None) == -1
+    assert lib.flic_decode_submit(None, None, None, 0, None, 0) == -1
+    assert lib.flic_strerror(-8).decode().startswith("an operation submitted")
