@@ -488,7 +488,10 @@ def main():
     hbm, peak_src = peaks()
     secondary = None
     if not args.no_secondary and args.workload == "C2x64":
-        secondary = secondary_lines(D, codec, args, hbm)
+        try:
+            secondary = secondary_lines(D, codec, args, hbm)
+        except Exception as e:  # the headline line must survive a failure in a side workload
+            secondary = {"error": f"{type(e).__name__}: {e}"[:300]}
     clocks = sampler.stop() if sampler else None  # sampled across warm-up, the device-timed steps, e2e and secondary
     if D.rank != 0:
         D.close()
