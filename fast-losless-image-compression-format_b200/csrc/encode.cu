@@ -433,22 +433,27 @@ __global__ void __launch_bounds__(32) k_tables(const uint16_t *__restrict__ hist
         const int n = __shfl_sync(0xFFFFFFFFu, myn, j);
         const uint64_t na = shfl64(mya, j), nb = shfl64(myb, j);
         reinterpret_cast<uint2 *>(s.lenS)[lane] = make_uint2(0u, 0u);
-        uint32_t nx = 0, prevnum = 0, start = 0;
+        uint32_t nx = 0, prevnum = 0;
+        uint32_t thr[kL + 2];  // thr[l] = number of ranks whose code is at least l bits long (the rarest ranks get the longest codes)
 #pragma unroll
         for (int l = 1; l <= kL; ++l) {
             nx = (nx + prevnum) << 1;
             if (lane == 0) s.next[l] = nx;
             prevnum = cnt_get(na, nb, l);
+            thr[l] = prevnum;
         }
+        thr[kL + 1] = 0;
 #pragma unroll
-        for (int l = kL; l >= 1; --l) {  // rarest ranks first -> longest codes
-            const uint32_t c = cnt_get(na, nb, l);
-            for (uint32_t i = start + lane; i < start + c; i += 32) s.lenR[i] = (uint8_t)l;
-            start += c;
-        }
+        for (int l = kL; l >= 1; --l) thr[l] += thr[l + 1];
         __syncwarp();
         if (n >= 2) {
-            for (int i = lane; i < n; i += 32) s.lenS[s.ord[j][i]] = s.lenR[i];
+            // rank i (ascending weight) has length kL - #{t in 2..kL : i >= thr[t]}: ten compares instead of ten fill loops
+            for (int i = lane; i < n; i += 32) {
+                uint32_t l = (uint32_t)kL;
+#pragma unroll
+                for (int t = kL; t >= 2; --t) l -= (uint32_t)i >= thr[t] ? 1u : 0u;
+                s.lenS[s.ord[j][i]] = (uint8_t)l;
+            }
         } else if (n == 1 && lane == 0) {
             s.lenS[s.ord[j][0]] = (uint8_t)kLenSole;
         }
