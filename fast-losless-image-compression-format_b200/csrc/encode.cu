@@ -272,7 +272,6 @@ struct TabSmemT {
     uint16_t A[BPW * kTabPitch];  // merge arrays, one row per lane-owned block; odd word pitch = conflict-free in step
     uint8_t ord[BPW][256];   // sorted symbol order per block
     uint8_t lenS[256];      // code length per SYMBOL of the block being finished
-    uint8_t lenR[256];      // code length per sorted RANK
     uint32_t next[16];      // first canonical code per length
 };
 

@@ -226,6 +226,44 @@ def test_random_geometries(codec, oracle):
         assert np.array_equal(oracle.decode(got, img.shape), img), (trial, w, h, c, flags, kind)
 
 
+@pytest.mark.parametrize("flags", [0x21, 0x41])
+def test_corrupt_streams_never_crash_layouts(codec, oracle, flags):
+    """The same damage sweep for the two optional layouts.  ONE_STREAM is the delicate one: its decoder follows code
+    lengths through the stream with no row structure to bound it, so every loop has to be bounded by validated
+    header fields (chains by the block's word count, rounds by the thread count, symbols by the block's pixel
+    count) and a damaged code table must not be able to stall a chain (zero-length LUT entries are made to consume
+    a bit)."""
+    import flic_b200 as flic
+    rng = np.random.default_rng(78 + flags)
+    img = cases.gradient(384, 96, 4, 45)
+    good = codec.encode(img, flags)
+    outcomes = {0: 0, -3: 0}
+    for trial in range(60):
+        bad = good.copy()
+        lo = 0 if trial % 3 else 32
+        for _ in range(int(rng.integers(1, 12))):
+            i = int(rng.integers(lo, bad.size))
+            bad[i] ^= np.uint8(rng.integers(1, 256))
+        try:
+            out = codec.decode(bad)
+            assert out.shape == img.shape
+            outcomes[0] += 1
+        except flic.FlicError as e:
+            assert e.code == -3, e
+            outcomes[-3] += 1
+        assert oracle.decode_rc(bad, img.shape) in (0, -3)
+    assert outcomes[0] and outcomes[-3]
+    # a code table with holes (an incomplete code): the first block's length nibbles zeroed except two symbols
+    nb = int(np.frombuffer(good[20:24], np.uint32)[0])
+    first_block = 32 + 4 * (nb + 1) + 4 * int(np.frombuffer(good[32:36], np.uint32)[0])
+    bad = good.copy(); bad[first_block: first_block + 128] = 0; bad[first_block] = 0x33   # symbols 0 and 1: 3 bits each
+    try:
+        codec.decode(bad)
+    except flic.FlicError as e:
+        assert e.code == -3
+    assert np.array_equal(codec.decode(good), img)
+
+
 def test_corrupt_streams_never_crash(codec, oracle):
     """Random damage anywhere in a stream — directory, length nibbles, row word counts, flat words, payload:
     the decoder answers OK (garbage pixels) or FLIC_E_FORMAT, never faults, and the context stays usable.
