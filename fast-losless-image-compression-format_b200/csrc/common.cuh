@@ -1,5 +1,6 @@
-// common.cuh — geometry, format constants and the in-register row-residual
-// routine shared by the histogram and pack kernels.  sm_100a only.
+// common.cuh — geometry, format constants, the in-register row-residual routine
+// shared by the histogram kernels and the fused encoder, and the launchers the C
+// ABI (api.cu) calls.  sm_100a only.
 //
 // Nothing here follows the reference's source (licensing gate, LICENSING.md);
 // the format is the provisional FLP0 bitstream specified in DESIGN.md.

@@ -7,9 +7,10 @@
 // 2^kL-entry shared-memory LUT (every lane its own 32 entries), exclusive-scan
 // the row word counts into per-lane stream offsets, then every lane runs a LUT
 // decode whose per-symbol work is shaped around the ALU pipe (see BitReader),
-// undoes the left predictor in 16-bit-lane running sums and hands RGBA pixels to
-// the TMA unit in 32 x 64 B tiles (other layouts: 256-/128-bit stores).  Column 0
-// is a byte-wise prefix sum down the rows, done as a warp scan.
+// undoes the left predictor in 16-bit-lane running sums and hands RGBA / RGB pixels
+// to the TMA unit in 32 x 64 B / 32 x 96 B tiles (other layouts: 256-/128-bit
+// stores).  Column 0 is a byte-wise prefix sum down the rows, done as a warp scan.
+// The ONE_STREAM layout has its own decoder (decode_one.cu).
 //
 // Format: DESIGN.md §FLP0 (provisional; not the reference's bitstream).
 #include <cstring>
