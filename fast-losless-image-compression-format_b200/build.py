@@ -9,7 +9,8 @@ _DEPS = _SOURCES + ["csrc/common.cuh", "csrc/decode_common.cuh", "../include/fli
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libflicb200.so")
+    # FLIC_LIB: A/B experiments load another build of the same sources (tools/ab.sh); never set in tests or the bench
+    return os.environ.get("FLIC_LIB") or os.path.join(_HERE, "libflicb200.so")
 
 
 def _stale(out: str) -> bool:
@@ -19,16 +20,20 @@ def _stale(out: str) -> bool:
     return any(os.path.getmtime(os.path.join(_HERE, d)) > t for d in _DEPS)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA engine + C ABI. nvcc cross-compiles without a GPU."""
-    out = library_path()
-    if not force and not _stale(out):
-        return out
+def build_library(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
+    """Compile the CUDA engine + C ABI. nvcc cross-compiles without a GPU.
+    out / defines: an A/B build of the same sources under another name (tools/ab.py), e.g. defines=("FLIC_SUBHIST=8",)."""
+    if out is None:
+        out = library_path()
+        if os.environ.get("FLIC_LIB"):
+            return out
+        if not force and not _stale(out):
+            return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [
         nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
         "-Xcompiler", "-fPIC", "-shared", "-o", out,
-    ] + _SOURCES
+    ] + ["-D" + d for d in defines] + _SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, cwd=_HERE, capture_output=True, text=True)

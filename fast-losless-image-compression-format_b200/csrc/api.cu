@@ -489,8 +489,9 @@ extern "C" int flic_get_kernel_times(flic_ctx *ctx, double ms[FLIC_K_COUNT], uin
 
 static int report_device_errors(flic_ctx *ctx, uint32_t e) {
     if (!e) return FLIC_OK;
-    snprintf(ctx->msg, sizeof ctx->msg, "device error bits 0x%x%s%s%s%s", e, (e & kErrCapacity) ? " capacity" : "",
-             (e & kErrSlot) ? " slot-overrun" : "", (e & kErrFormat) ? " format" : "", (e & kErrRange) ? " payload-exceeds-u32-words" : "");
+    snprintf(ctx->msg, sizeof ctx->msg, "device error bits 0x%x%s%s%s%s%s", e, (e & kErrCapacity) ? " capacity" : "",
+             (e & kErrSlot) ? " slot-overrun" : "", (e & kErrFormat) ? " format" : "", (e & kErrRange) ? " payload-exceeds-u32-words" : "",
+             (e & kErrLayout) ? " shared-memory-layout" : "");
     if (e & kErrFormat) return FLIC_E_FORMAT;
     if (e & kErrCapacity) return FLIC_E_CAPACITY;
     if (e & kErrRange) return FLIC_E_UNSUPPORTED;

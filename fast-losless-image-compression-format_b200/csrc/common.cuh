@@ -31,6 +31,7 @@ constexpr uint32_t kErrCapacity = 1u;
 constexpr uint32_t kErrFormat = 4u;
 constexpr uint32_t kErrSlot = 8u;  // a block outgrew the slot k_slots computed for it (internal error)
 constexpr uint32_t kErrRange = 16u;  // an image's payload does not fit the container's u32 word offsets
+constexpr uint32_t kErrLayout = 32u;  // a kernel's shared-memory layout assumption does not hold (internal error)
 
 __host__ __device__ __forceinline__ bool one_stream(uint32_t flags) { return (flags & FLIC_FLAG_ONE_STREAM) != 0; }
 __host__ __device__ __forceinline__ int blk_hdr_words(uint32_t flags) { return one_stream(flags) ? kBlkHdrWords1 : kBlkHdrWords; }

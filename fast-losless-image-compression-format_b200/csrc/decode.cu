@@ -22,6 +22,8 @@
 namespace flic {
 
 constexpr int kDecWarps = 4;
+constexpr int kLutPad = 5 * 1024;  // offset of the LUTs in k_decode's shared struct: >= scratch + records, and 1 KB (mod 2 KB)
+static_assert(sizeof(LutScratch) * kDecWarps + 32 * kDecWarps <= kLutPad && kLutPad % 2048 == 1024, "k_decode shared layout");
 // stream lines are pulled into L1 this many chunks of average consumption ahead (measured: 0 -> 2 is -7 %)
 constexpr uint32_t kPrefetchChunks = 2;
 // ... and the head of a block is pulled towards L2 while its LUT is built.  2 KB: more (the whole block)
@@ -62,6 +64,8 @@ struct BitReader {
 
 struct RowStream {
     const uint32_t *blk;     // block payload (warp-uniform)
+    const char *lane0;       // the lane's word 0 in the interleaved region: word k is at lane0 + k * stride4
+    uint32_t stride4;        // stride in bytes
     uint32_t ib, stride, tb; // element offsets: interleaved base, stride, tail base (pre-biased by -minw)
     uint32_t minw, words;
     __device__ __forceinline__ uint32_t eo(uint32_t i) const { return i < minw ? ib + i * stride : tb + i; }
@@ -83,7 +87,7 @@ __device__ __forceinline__ void refill(BitReader &r, const RowStream &rs) {
     //                                           n == 0 gives lo = 0)
     //   cn  += 32;  wq = next word;  k += 1
     if (kFast) {
-        const uint32_t *p = rs.blk + (rs.ib + r.k * rs.stride);
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(rs.lane0 + (uint64_t)r.k * rs.stride4);  // one IMAD.WIDE
         asm volatile(
             "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
             "and.b32 t, %2, 32;\n\t"
@@ -116,12 +120,14 @@ __device__ __forceinline__ void refill(BitReader &r, const RowStream &rs) {
     }
 }
 
-// Decodes one symbol; returns the LUT entry (len | sym << 8).  `luts` is the CTA's LUT array,
-// `wsel` = warp << 11 selects the warp's 2 KB table, `m2048` is the constant 2048 kept opaque
-// (a kernel argument) so that the shift is issued as IMAD.HI.
-__device__ __forceinline__ uint32_t get(BitReader &r, const char *luts, uint32_t wsel, uint32_t m2048) {
-    const uint32_t o = (__umulhi(r.hi, m2048) & 0x7FEu) | wsel;
-    const uint32_t e = *reinterpret_cast<const uint16_t *>(luts + o);
+// Decodes one symbol; returns the LUT entry (len | sym << 8).  `lut_s` is the shared-window address of
+// the warp's LUT, 2 KB-aligned, so (index & 0x7FE) | lut_s is the entry's complete address in ONE LOP3 and the
+// load needs no base add (a generic pointer + offset cost an extra IMAD.IADD per symbol); `m2048` is the
+// constant 2048 kept opaque (a kernel argument) so that the shift is issued as IMAD.HI.
+__device__ __forceinline__ uint32_t get(BitReader &r, uint32_t lut_s, uint32_t m2048) {
+    const uint32_t a = (__umulhi(r.hi, m2048) & 0x7FEu) | lut_s;
+    uint32_t e;  // (the LUT is complete, and fenced by __syncwarp, before any reader exists: plain asm, free to be scheduled)
+    asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(a));
     r.hi = __funnelshift_l(r.lo, r.hi, e);
     r.lo = __funnelshift_l(0u, r.lo, e);
     r.cn -= e;
@@ -171,8 +177,8 @@ template <int C, int FM> struct Chunk {
 
 // One chunk of U pixels: U*CS symbols with a refill check before every kSymsPerRefill-th.
 template <int C, bool SG, int FM, bool kFast>
-__device__ __forceinline__ void decode_chunk(BitReader &br, const RowStream &rs, Acc &acc, const char *luts,
-                                             uint32_t wsel, uint32_t m2048, uint32_t *o) {
+__device__ __forceinline__ void decode_chunk(BitReader &br, const RowStream &rs, Acc &acc, uint32_t lut_s,
+                                             uint32_t m2048, uint32_t *o) {
     constexpr int U = Chunk<C, FM>::U;
     int sidx = 0;  // compile-time after unrolling
 #pragma unroll
@@ -185,7 +191,7 @@ __device__ __forceinline__ void decode_chunk(BitReader &br, const RowStream &rs,
                 if ((FM >> ch) & 1) continue;
                 if (sidx % kSymsPerRefill == 0) refill<kFast>(br, rs);
                 ++sidx;
-                acc_add<C>(acc, ch, get(br, luts, wsel, m2048));
+                acc_add<C>(acc, ch, get(br, lut_s, m2048));
             }
             px[u] = acc_pixel<C, SG>(acc);
         }
@@ -216,10 +222,10 @@ __device__ __forceinline__ void acc_set(Acc &v, int ch, uint32_t val) {
 // 96-byte pitch are 2-way bank-conflicted, still four times fewer wavefronts than stores straight to global memory.
 // kTma selects the variant at compile time: 0 none, 4 RGBA, 3 RGB (each kernel carries only its own staging).
 template <int kTma> struct TileGeo {
-    static constexpr uint32_t kBytes = kTma == 3 ? 32u * 96u : 32u * 64u;
-    static constexpr uint32_t kStride = kBytes + 512;  // 512 B for the record; keeps the swizzle phase of the next tile
+    static constexpr uint32_t kBytes = kTma == 3 ? 32u * 96u : 32u * 64u;  // a multiple of 1 KB: every tile keeps the swizzle phase
 };
-struct TileRec { unsigned long long map; uint32_t x0b, y0, img, pad; };
+struct TileRec { unsigned long long map; uint32_t x0b, y0, img, pad[3]; };  // 32 bytes
+static_assert(sizeof(TileRec) == 32, "tile_flush addresses the warp's record as recs + 32 * warp");
 __device__ __forceinline__ void tile_put(uint32_t tile, int lane, int half, const uint32_t *o) {
     const uint32_t row = tile + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
@@ -238,16 +244,16 @@ __device__ __forceinline__ void tile_put3(uint32_t tile, int lane, int half, con
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a + 16u * c), "r"(o[4 * c]), "r"(o[4 * c + 1]), "r"(o[4 * c + 2]),
                      "r"(o[4 * c + 3]) : "memory");
 }
-template <uint32_t kRecAt>
-__device__ __forceinline__ void tile_flush(uint32_t tile, int lane, uint32_t xbyte, uint32_t amask) {
+// rec_s: shared address of the warp's TileRec (recomputed per flush from the warp index: no register lives across the loop)
+__device__ __forceinline__ void tile_flush(uint32_t tile, uint32_t rec_s, int lane, uint32_t xbyte, uint32_t amask) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
     __syncwarp(amask);
     if (lane == 0) {
         unsigned long long map;
         uint32_t x0b, y0, img;
-        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(map) : "r"(tile + kRecAt));
-        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x0b), "=r"(y0) : "r"(tile + kRecAt + 8));
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(img) : "r"(tile + kRecAt + 16));
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(map) : "r"(rec_s));
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x0b), "=r"(y0) : "r"(rec_s + 8));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(img) : "r"(rec_s + 16));
         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
                      "r"(x0b + xbyte), "r"(y0), "r"(img), "r"(tile) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -259,9 +265,9 @@ __device__ __forceinline__ void tile_wait(int lane, uint32_t amask) {  // the ti
 }
 
 template <int C, bool SG, int FM, int kTma>
-__device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel, uint32_t m2048, uint8_t *dst, int bwa,
+__device__ void decode_rows(const RowStream &rs, uint32_t lut_s, uint32_t m2048, uint8_t *dst, int bwa,
                             bool active, int aligned, int lane, uint32_t fmask, uint32_t fvals, uint32_t pfx,
-                            uint32_t tma /* the warp's tile, or 0 */) {
+                            uint32_t tma /* the warp's tile, or 0 */, uint32_t recs_s /* the CTA's TileRec array */) {
     constexpr int FMC = FM < 0 ? 0 : FM;
     constexpr int U = Chunk<C, FMC>::U, W = Chunk<C, FMC>::W;
     const uint32_t amask = __ballot_sync(0xFFFFFFFFu, active);
@@ -280,7 +286,7 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
             if ((fmask >> ch) & 1u) continue;
             if (sidx % kSymsPerRefill == 0) refill<false>(t, rs);
             ++sidx;
-            acc_add<C>(z, ch, get(t, luts, wsel, m2048));
+            acc_add<C>(z, ch, get(t, lut_s, m2048));
         }
         first = __byte_perm(z.a, z.b, 0x7351);
         if (C < 4) first &= (1u << (8 * (C & 3))) - 1u;
@@ -311,18 +317,18 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
                     const uint32_t kp = min(br.k + pf, rs.minw - 1u);
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(rs.blk + (rs.ib + kp * rs.stride)));
                 }
-                decode_chunk<C, SG, FMC, true>(br, rs, acc, luts, wsel, m2048, o);
+                decode_chunk<C, SG, FMC, true>(br, rs, acc, lut_s, m2048, o);
             }
             else
-                decode_chunk<C, SG, FMC, false>(br, rs, acc, luts, wsel, m2048, o);
+                decode_chunk<C, SG, FMC, false>(br, rs, acc, lut_s, m2048, o);
             uint8_t *d = dst + (size_t)x * C;
             const int half = (x / U) & 1;
             if (kTma == 4 && C == 4 && tma && (half == 1 || x + 2 * U <= bwa)) {  // chunk pairs go out as one TMA tile
                 if (half == 0) { if (x > 0) tile_wait(lane, amask); tile_put(tma, lane, 0, o); }
-                else { tile_put(tma, lane, 1, o); tile_flush<TileGeo<4>::kBytes>(tma, lane, (uint32_t)(x - U) * 4u, amask); }
+                else { tile_put(tma, lane, 1, o); tile_flush(tma, recs_s + 32u * (threadIdx.x >> 5), lane, (uint32_t)(x - U) * 4u, amask); }
             } else if (kTma == 3 && C == 3 && tma && (half == 1 || x + 2 * U <= bwa)) {
                 if (half == 0) { if (x > 0) tile_wait(lane, amask); tile_put3(tma, lane, 0, o); }
-                else { tile_put3(tma, lane, 1, o); tile_flush<TileGeo<3>::kBytes>(tma, lane, (uint32_t)(x - U) * 3u, amask); }
+                else { tile_put3(tma, lane, 1, o); tile_flush(tma, recs_s + 32u * (threadIdx.x >> 5), lane, (uint32_t)(x - U) * 3u, amask); }
             } else if (W == 8 && aligned == 2) {  // one 256-bit store: a whole 32-byte sector per lane and half the LSU wavefronts
                 asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]),
                              "r"(o[3]), "r"(o[4 % W]), "r"(o[5 % W]), "r"(o[6 % W]), "r"(o[7 % W])
@@ -344,7 +350,7 @@ __device__ void decode_rows(const RowStream &rs, const char *luts, uint32_t wsel
         for (int ch = 0; ch < C; ++ch) {
             if ((fmask >> ch) & 1u) continue;  // warp-uniform
             refill<false>(br, rs);
-            acc_add<C>(acc, ch, get(br, luts, wsel, m2048));
+            acc_add<C>(acc, ch, get(br, lut_s, m2048));
         }
         store_bytes<C>(dst + (size_t)x * C, acc_pixel<C, SG>(acc));
         acc_clean(acc);
@@ -358,14 +364,29 @@ __global__ void __launch_bounds__(kDecWarps * 32, kTma == 3 ? 8 : 10) k_decode(c
                                                           const unsigned long long *__restrict__ offsets, Geo g,
                                                           uint8_t *__restrict__ pixels, uint32_t *err, uint32_t m2048, uint32_t pf, uint32_t pf2,
                                                           const __grid_constant__ CUtensorMap tmap) {
-    __shared__ __align__(1024) uint8_t tiles[kTma ? kDecWarps : 1][kTma ? TileGeo<kTma>::kStride : 16];  // TMA store staging, 32 rows x 64 / 96 B per warp (+ record)
-    __shared__ __align__(16) uint16_t luts[kDecWarps][kLutSize];
-    __shared__ LutScratch scratch[kDecWarps];
+    // ONE struct, so the order is ours.  get() ORs a LUT index into the warp's LUT address, which therefore has to be
+    // 2 KB-aligned in the shared WINDOW; static shared memory starts 1 KB into it (the driver's reserved KB), so the LUTs
+    // sit at an offset of 1 KB (mod 2 KB) — checked below, a violation is reported, never decoded through.
+    struct Smem {
+        LutScratch scratch[kDecWarps];
+        TileRec recs[kDecWarps];
+        uint8_t pad[kLutPad - sizeof(LutScratch) * kDecWarps - sizeof(TileRec) * kDecWarps];
+        uint16_t luts[kDecWarps][kLutSize];
+        uint8_t tiles[kTma ? kDecWarps : 1][kTma ? TileGeo<kTma>::kBytes : 16];  // TMA store staging, 32 rows x 64 / 96 B per warp
+    };
+    static_assert(offsetof(Smem, luts) % 2048 == 1024 && offsetof(Smem, tiles) % 1024 == 0, "see above");
+    __shared__ __align__(1024) Smem sm;
+    auto &luts = sm.luts; auto &tiles = sm.tiles; auto &scratch = sm.scratch;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t gb = (uint64_t)blockIdx.x * kDecWarps + warp;
     if (gb >= (uint64_t)g.n * g.nb) return;
     const BlockPos p = block_pos(g, gb);
     uint16_t *lut = luts[warp];
+    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(lut);
+    if (lut_s & 2047u) {  // the layout assumption above does not hold on this driver: refuse
+        if (lane == 0) atomicOr(err, kErrLayout);
+        return;
+    }
 
     const unsigned long long sbeg = offsets[p.img], send = offsets[p.img + 1];
     const uint32_t *sw = streams + (sbeg >> 2);
@@ -411,6 +432,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, kTma == 3 ? 8 : 10) k_decode(c
     }
     RowStream rs;
     rs.blk = blk; rs.ib = kBlkHdrWords + lane; rs.stride = p.bha;
+    rs.lane0 = reinterpret_cast<const char *>(blk + rs.ib); rs.stride4 = 4u * p.bha;
     rs.tb = kBlkHdrWords + minw * p.bha + (incl - rc) - lane * minw - minw;
     rs.minw = minw; rs.words = active ? rc : 0u;
     uint8_t *dst = pixels + (uint64_t)p.img * g.img_stride + (uint64_t)(p.y0 + lane) * g.pitch +
@@ -421,16 +443,15 @@ __global__ void __launch_bounds__(kDecWarps * 32, kTma == 3 ? 8 : 10) k_decode(c
     if (kTma && (int)g.c == kTma) {
         tp = (uint32_t)__cvta_generic_to_shared(&tiles[warp][0]);
         if (lane == 0) {
-            TileRec *rec = reinterpret_cast<TileRec *>(&tiles[warp][kTma ? TileGeo<kTma>::kBytes : 0]);
+            TileRec *rec = &sm.recs[warp];
             rec->map = reinterpret_cast<unsigned long long>(&tmap);
             rec->x0b = p.x0 * g.c; rec->y0 = p.y0; rec->img = p.img;
         }
         __syncwarp();
     }
-    const char *lb = reinterpret_cast<const char *>(&luts[0][0]);
-    const uint32_t wsel = (uint32_t)warp << 11;
-    static_assert(kLutSize * 2 == 2048, "wsel assumes 2 KB per warp LUT");
-#define FLIC_ROWS(C, SG, FM) decode_rows<C, SG, FM, kTma>(rs, lb, wsel, m2048, dst, (int)p.bwa, active, aligned, lane, fmask, fvals, pf, tp)
+    static_assert(kLutSize * 2 == 2048, "get() assumes a 2 KB-aligned, 2 KB LUT per warp");
+    const uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(&sm.recs[0]);
+#define FLIC_ROWS(C, SG, FM) decode_rows<C, SG, FM, kTma>(rs, lut_s, m2048, dst, (int)p.bwa, active, aligned, lane, fmask, fvals, pf, tp, recs_s)
     if (fmask == 0) {
         switch (g.c) {
             case 1: FLIC_ROWS(1, false, 0); break;

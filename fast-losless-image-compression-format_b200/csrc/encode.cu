@@ -26,6 +26,7 @@
 // LICENSING.md).  Byte-exact CPU model: oracle/flp0_oracle.c (tests only).
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include <cuda.h>  // CUtensorMap (type only; the driver entry point is resolved in api.cu)
 
@@ -33,14 +34,24 @@
 
 namespace flic {
 
-// byte j of w, times four (a u32 table offset), in two instructions
-__device__ __forceinline__ uint32_t byte_x4(uint32_t w, int j) {
-    return j == 0 ? (w << 2) & 0x3FCu : (w >> (8 * j - 2)) & 0x3FCu;
-}
-
 // ---------------------------------------------------------------- k_histograms
 constexpr int kEncThreads = 256;
 constexpr int kEncWarps = kEncThreads / 32;
+
+// Sub-histograms per CTA: warp w counts into sub-histogram w % kSubHist.  What bounds the kernel is the LSU data pipe
+// (ncu: l1tex__data_pipe_lsu_wavefronts 73 % of peak), and eight private copies cost 64 wavefronts to clear and 64 to sum,
+// an eighth of the CTA's shared-memory traffic; shared atomics from different warps are separate instructions either way.
+// Measured (k_histograms ms, 8 / 4 / 2 copies): 4K RGBA 0.691 / 0.689 / 0.683, noise 1.129 / 1.127 / 1.112, 1080p RGB
+// 0.334 / 0.331 / 0.339.
+template <int C> struct SubHist { static constexpr int k = C == 3 ? 4 : 2; };
+
+// ++hist[byte j of w], `base_s` = shared-window address of the warp's 1 KB-aligned sub-histogram: the shift, ONE
+// LOP3 for (x & 0x3FC) | base and the ATOMS.POPC.INC — a generic pointer + offset cost one more add per symbol.
+__device__ __forceinline__ void hist_inc(uint32_t base_s, uint32_t w, int j) {
+    const uint32_t x = j == 0 ? (w << 2) : (w >> (8 * j - 2));
+    const uint32_t a = (x & 0x3FCu) | base_s;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
+}
 
 // resid (optional): the "residual plane" — per block a tile [32 rows][32 lanes][C words] of residual
 // bytes in the lane order above — so that k_pack does not recompute prediction (the kernels are
@@ -68,7 +79,9 @@ template <int C, bool SG, bool kTma>
 __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__restrict__ pixels, Geo g,
                                                             uint16_t *__restrict__ hist, uint32_t *__restrict__ resid,
                                                             uint2 *__restrict__ flat, const __grid_constant__ CUtensorMap tmap) {
-    __shared__ __align__(16) uint32_t sh[kEncWarps][256];
+    constexpr int kSubHist = SubHist<C>::k;
+    static_assert(kSubHist >= 1 && kSubHist <= kEncWarps && (kSubHist & (kSubHist - 1)) == 0, "power of two");
+    __shared__ __align__(1024) uint32_t sh[kSubHist][256];  // 1 KB-aligned rows: hist_inc() ORs the offset into the base
     __shared__ __align__(128) uint32_t ptile[kTma ? kBH * 32 * C : 4];
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t s_or[C], s_first;
@@ -87,8 +100,10 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__
 
     {
         uint4 *z = reinterpret_cast<uint4 *>(&sh[0][0]);
+        if (kSubHist * 256 / 4 >= kEncThreads) {
 #pragma unroll
-        for (int i = 0; i < kEncWarps * 256 / 4 / kEncThreads; ++i) z[tid + i * kEncThreads] = make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < kSubHist * 256 / 4 / kEncThreads; ++i) z[tid + i * kEncThreads] = make_uint4(0, 0, 0, 0);
+        } else if (tid < kSubHist * 256 / 4) z[tid] = make_uint4(0, 0, 0, 0);
     }
     if (tid < C) s_or[tid] = 0;
     if (kTma) {
@@ -194,7 +209,8 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__
             if (lane == 0 && o) atomicOr(&s_or[j], o);
         }
     }
-    char *my = reinterpret_cast<char *>(sh[warp]);
+    const uint32_t my = (uint32_t)__cvta_generic_to_shared(sh[warp & (kSubHist - 1)]);
+    if (my & 1023u) __trap();  // hist_inc needs 1 KB-aligned sub-histograms in the shared window (cannot happen: fail loudly)
     uint32_t zero_rows = 0;  // RGBA rows whose alpha residuals are all zero (an opaque plane): counted, not looked up
 #pragma unroll
     for (int q = 0; q < kBH / kEncWarps; ++q) {
@@ -202,18 +218,18 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__
                                  ((res[q][0] | res[q][1 % C] | res[q][2 % C] | res[q][3 % C]) & 0xFF000000u) == 0)) {
 #pragma unroll
             for (int j = 0; j < 4 * C; ++j)
-                if ((j & 3) != 3) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[q][j >> 2], j & 3)), 1u);
+                if ((j & 3) != 3) hist_inc(my, res[q][j >> 2], j & 3);
             ++zero_rows;
         } else if (nv[q] == 4 * C) {
 #pragma unroll
-            for (int j = 0; j < 4 * C; ++j) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[q][j >> 2], j & 3)), 1u);
+            for (int j = 0; j < 4 * C; ++j) hist_inc(my, res[q][j >> 2], j & 3);
         } else if (nv[q] > 0) {
 #pragma unroll
             for (int j = 0; j < 4 * C; ++j)
-                if (j < nv[q]) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[q][j >> 2], j & 3)), 1u);
+                if (j < nv[q]) hist_inc(my, res[q][j >> 2], j & 3);
         }
     }
-    if (C == 4 && lane == 0 && zero_rows) atomicAdd(&sh[warp][0], zero_rows * (uint32_t)kBW);
+    if (C == 4 && lane == 0 && zero_rows) atomicAdd(&sh[warp & (kSubHist - 1)][0], zero_rows * (uint32_t)kBW);
     __syncthreads();
     if (kTma && resid && tid == 0) {
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(resid + gb * (uint64_t)(kBH * 32 * C)),
@@ -222,7 +238,7 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__
     }
     uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < kEncWarps; ++k) s += sh[k][tid];
+    for (int k = 0; k < kSubHist; ++k) s += sh[k][tid];
     {   // flat channels (FLP0 §2b): T = per channel byte, the OR of all its residual bytes bar the first pixel's
         uint32_t T;
         if (C == 4) T = s_or[0];
@@ -719,6 +735,19 @@ __device__ __forceinline__ uint32_t quad_of(uint32_t w, int first, int nv, uint3
     return __umulhi(e0 + e1 + sb, pm.m8);
 }
 
+// The opaque-alpha RGBA word: three symbols, at most 3 * kL = 30 bits — the group is ONE register, it can only
+// touch the word it ends in and the one before (two RED.OR, no "longer than 32 bits?" vote).
+static_assert(3 * kL <= 32, "quad3 returns the group in one word");
+__device__ __forceinline__ uint32_t quad3(uint32_t w, const uint32_t *tab, const PackMul &pm, uint32_t &q) {
+    const char *t = reinterpret_cast<const char *>(tab);
+    const uint32_t e0 = *reinterpret_cast<const uint32_t *>(t + ((w << 2) & 0x3FCu));
+    const uint32_t e1 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m26) & 0x3FCu));
+    const uint32_t e2 = *reinterpret_cast<const uint32_t *>(t + (__umulhi(w, pm.m18) & 0x3FCu));
+    const uint32_t pa = ((e0 << __umulhi(e1, pm.m8)) | e1) & 0xFFFFFu;
+    q = (pa << __umulhi(e2, pm.m8)) | (e2 & 0xFFFFFFu);
+    return __umulhi(e0 + e1 + e2, pm.m8);
+}
+
 template <int C>
 __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restrict__ resid, Geo g,
                                                       const uint16_t *__restrict__ table,
@@ -772,38 +801,67 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     // counts places them, and every group is OR-ed straight into the zeroed staging row at its END bit
     // position: group << ((32 - end) & 31) occupies the word the group ends in and the one or two before.
     const uint32_t sstage = (uint32_t)__cvta_generic_to_shared(stage);
+    // kNarrow: an opaque-alpha RGBA block (flat mask 8) — every group is at most 30 bits (quad3, or the generic builder with
+    // the alpha byte skipped on ragged lanes) and fits one register.  Two instances of the whole row loop, chosen once per
+    // block (1.156 -> 1.065 ms on the 4K RGBA batch).  Measured side effect, unexplained by the SASS (the wide instance's
+    // hot path is instruction-for-instruction the one of a build without the narrow instance): blocks that take the wide
+    // instance pack 4 % slower than in such a build (noise batch 1.755 -> 1.83 ms); neither the order of the two
+    // instances, a smaller unroll, nor moving the rare ragged rows out of line changed that.
+    auto pack_rows = [&](auto narrow_c) {
+        constexpr bool kNarrow = decltype(narrow_c)::value;
 #pragma unroll
-    for (int q = 0; q < kBH / kEncWarps; ++q) {
-        const int r = warp + kEncWarps * q;
-        uint32_t cur[C];
+        for (int q = 0; q < kBH / kEncWarps; ++q) {
+            const int r = warp + kEncWarps * q;
+            uint32_t cur[C];
 #pragma unroll
-        for (int j = 0; j < C; ++j) cur[j] = nxt[j];
-        if (q + 1 < kBH / kEncWarps) load_row(r + kEncWarps, nxt);  // next row's residuals fly while this one packs
-        const int nv = r < (int)p.bha ? nvfull : 0;
-        uint32_t qlo[C], qhi[C], ql[C], nbits = 0;
-        if (nv == 4 * C && fl.x == 0) {
+            for (int j = 0; j < C; ++j) cur[j] = nxt[j];
+            if (q + 1 < kBH / kEncWarps) load_row(r + kEncWarps, nxt);  // next row's residuals fly while this one packs
+            const int nv = r < (int)p.bha ? nvfull : 0;
+            uint32_t qlo[C], qhi[C], ql[C], nbits = 0;
+            if (kNarrow && nv == 4 * C) {  // three table reads per pixel
 #pragma unroll
-            for (int j = 0; j < C; ++j) { ql[j] = quad_of<true, 0>(cur[j], 4 * j, 4 * C, 0u, tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
-        } else if (nv == 4 * C && C == 4 && fl.x == 8u) {  // opaque-alpha RGBA: three table reads per pixel
+                for (int j = 0; j < C; ++j) { ql[j] = quad3(cur[j], tab, pm, qlo[j]); nbits += ql[j]; }
+            } else if (!kNarrow && nv == 4 * C && fl.x == 0) {
 #pragma unroll
-            for (int j = 0; j < C; ++j) { ql[j] = quad_of<true, 8>(cur[j], 4 * j, 4 * C, 8u, tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
-        } else {
+                for (int j = 0; j < C; ++j) { ql[j] = quad_of<true, 0>(cur[j], 4 * j, 4 * C, 0u, tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+            } else {
 #pragma unroll
-            for (int j = 0; j < C; ++j) { ql[j] = quad_of<false, -1>(cur[j], 4 * j, nv, skip[j], tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+                for (int j = 0; j < C; ++j) { ql[j] = quad_of<false, -1>(cur[j], 4 * j, nv, skip[j], tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
+            }
+            const uint32_t incl = warp_incl_scan(nbits, lane);
+            if (lane == 31) rwc[r] = (incl + 31u) >> 5;
+            // nb = -(bit address in shared memory of the lane's next free bit); its low 5 bits are the shift
+            uint32_t nb = 0u - (8u * (sstage + 4u * (uint32_t)(r * kStagePitch + kStagePad)) + (incl - nbits));
+            if (kNarrow) {
+                // What bounds this kernel is the LSU data pipe (ncu: 77 % of peak, a quarter of it these RED.ORs at ~2.4
+                // wavefronts each), so two groups are first joined into one string of at most 60 bits: two RED.ORs per
+                // PAIR, and a third only from the lanes whose string reaches a third word.
+#pragma unroll
+                for (int j = 0; j + 1 < C; j += 2) {
+                    const uint32_t l1 = ql[j + 1];
+                    const uint32_t plo = (qlo[j] << l1) | qlo[j + 1];        // l1 <= 30
+                    const uint32_t phi = __funnelshift_l(qlo[j], 0u, l1);    // qlo[j] >> (32 - l1); 0 when l1 == 0
+                    nb -= ql[j] + l1;
+                    const uint32_t a = ((31u - nb) >> 3) & ~3u;  // byte address one past the word the string ends in
+                    red_or_shared(a, -4, __funnelshift_l(0u, plo, nb));
+                    red_or_shared(a, -8, __funnelshift_l(plo, phi, nb));
+                    const uint32_t w2 = __funnelshift_l(phi, 0u, nb);
+                    if (w2) red_or_shared(a, -12, w2);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    nb -= ql[j];
+                    const uint32_t a = ((31u - nb) >> 3) & ~3u;  // byte address one past the word the group ends in
+                    red_or_shared(a, -4, __funnelshift_l(0u, qlo[j], nb));
+                    red_or_shared(a, -8, __funnelshift_l(qlo[j], qhi[j], nb));
+                    if (__any_sync(0xFFFFFFFFu, ql[j] > 32u)) red_or_shared(a, -12, __funnelshift_l(qhi[j], 0u, nb));
+                }
+            }
         }
-        const uint32_t incl = warp_incl_scan(nbits, lane);
-        if (lane == 31) rwc[r] = (incl + 31u) >> 5;
-        // nb = -(bit address in shared memory of the lane's next free bit); its low 5 bits are the shift
-        uint32_t nb = 0u - (8u * (sstage + 4u * (uint32_t)(r * kStagePitch + kStagePad)) + (incl - nbits));
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            nb -= ql[j];
-            const uint32_t a = ((31u - nb) >> 3) & ~3u;  // byte address one past the word the group ends in
-            red_or_shared(a, -4, __funnelshift_l(0u, qlo[j], nb));
-            red_or_shared(a, -8, __funnelshift_l(qlo[j], qhi[j], nb));
-            if (__any_sync(0xFFFFFFFFu, ql[j] > 32u)) red_or_shared(a, -12, __funnelshift_l(qhi[j], 0u, nb));
-        }
-    }
+    };
+    if (C == 4 && fl.x == 8u) pack_rows(std::true_type{});
+    else pack_rows(std::false_type{});
     __syncthreads();
 
     // FLP0 §7: the block's slot (position and size) was fixed by k_slots from the histogram and the code
@@ -1084,8 +1142,8 @@ __device__ __forceinline__ unsigned long long ld_status(const unsigned long long
 }
 
 struct FusedSmem {
+    union { uint32_t sh[kEncWarps][256]; TabScratch t; } u;  // first: the sub-histograms must be 1 KB-aligned (hist_inc)
     uint32_t tile[kBH * kStagePitch];  // per row: residual words (word j of lane L at j*32 + L), then the packed row
-    union { uint32_t sh[kEncWarps][256]; TabScratch t; } u;
     uint32_t tab[256];
     uint8_t nib[256];
     uint32_t rwc[kBH], rowoff[kBH], rbit0[kBH + 1];  // words per row, word offset of each row's tail, first bit of each row
@@ -1099,7 +1157,7 @@ __global__ void __launch_bounds__(kEncThreads, kFusedCtas)
 k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ streams, uint64_t capacity_words,
          unsigned long long *__restrict__ dirE, unsigned long long *status, unsigned long long *ticket,
          unsigned long long ticket_base, uint32_t epoch, uint32_t *err, PackMul pm, unsigned long long *phase_clk) {
-    __shared__ __align__(16) FusedSmem sm;
+    __shared__ __align__(1024) FusedSmem sm;
     // phase_clk (debug, normally null): thread 0 of every CTA adds the cycles it spent per phase
     long long t_prev = phase_clk ? clock64() : 0;
 #define FLIC_PHASE(i)                                                       \
@@ -1157,7 +1215,8 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
             uint32_t orw[C];
 #pragma unroll
             for (int j = 0; j < C; ++j) orw[j] = 0;
-            char *my = reinterpret_cast<char *>(sm.u.sh[warp]);
+            const uint32_t my = (uint32_t)__cvta_generic_to_shared(sm.u.sh[warp]);
+            if (my & 1023u) __trap();  // hist_inc needs 1 KB-aligned sub-histograms (cannot happen: fail loudly)
             uint32_t zero_rows = 0;
 #pragma unroll
             for (int q = 0; q < kBH / kEncWarps; ++q) {
@@ -1183,15 +1242,15 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
                     if (C == 4 && __all_sync(0xFFFFFFFFu, lane_full && ((res[0] | res[1 % C] | res[2 % C] | res[3 % C]) & 0xFF000000u) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 4 * C; ++j)
-                            if ((j & 3) != 3) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[j >> 2], j & 3)), 1u);
+                            if ((j & 3) != 3) hist_inc(my, res[j >> 2], j & 3);
                         ++zero_rows;  // an all-zero alpha row (opaque plane): counted once, not looked up
                     } else if (lane_full) {
 #pragma unroll
-                        for (int j = 0; j < 4 * C; ++j) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[j >> 2], j & 3)), 1u);
+                        for (int j = 0; j < 4 * C; ++j) hist_inc(my, res[j >> 2], j & 3);
                     } else if (nvl > 0) {
 #pragma unroll
                         for (int j = 0; j < 4 * C; ++j)
-                            if (j < nvl) atomicAdd(reinterpret_cast<uint32_t *>(my + byte_x4(res[j >> 2], j & 3)), 1u);
+                            if (j < nvl) hist_inc(my, res[j >> 2], j & 3);
                     }
                 }
             }
