@@ -366,20 +366,22 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
     // AUTO: below kAutoBlocks the job is a latency chain (launches, one wave of CTAs) and the two-launch fused path
     // wins; above it the staged pipeline's higher issue efficiency does (measured: DESIGN.md §5)
     constexpr uint64_t kAutoBlocks = 4096;
-    const bool want_staged = ctx->encoder == FLIC_ENCODER_STAGED || (ctx->encoder == FLIC_ENCODER_AUTO && (uint64_t)n * g.nb >= kAutoBlocks);
-    const bool staged = want_staged && !(flags & (FLIC_FLAG_ONE_STREAM | FLIC_FLAG_EXACT));
+    const bool staged = ctx->encoder == FLIC_ENCODER_STAGED || (ctx->encoder == FLIC_ENCODER_AUTO && (uint64_t)n * g.nb >= kAutoBlocks);
+    const bool exact = (flags & FLIC_FLAG_EXACT) != 0;
     CU(cudaSetDevice(ctx->device));
     rc = ensure_workspace(ctx, (uint64_t)n * g.nb, staged);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if (ctx->ws_used && ctx->ws_stream != s) CU(cudaStreamWaitEvent(s, ctx->ev_ws, 0));  // one workspace per context
     const uint64_t cap_words = capacity_bytes / 4;
-    if (!staged) {
-        // fused single pass (k_encode) + headers/directories (k_finalize)
+    if (!staged || exact) {  // a launch that looks back: a fresh epoch on the status array
         if (++ctx->fused_epoch >= (1u << 22)) {  // the 22-bit epoch wrapped: start over on a clean status array
             CU(cudaMemsetAsync(ctx->d_status, 0, ctx->ws_blocks * sizeof(unsigned long long), s));
             ctx->fused_epoch = 1;
         }
+    }
+    if (!staged) {
+        // fused single pass (k_encode) + headers/directories (k_finalize)
         unsigned grid;
         { KernelTimer t(ctx, FLIC_K_ENCODE, s);
           grid = launch_encode_fused(d_pixels, g, (uint32_t *)d_streams, cap_words, ctx->d_dirE, ctx->d_status, ctx->d_ticket,
@@ -394,17 +396,28 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
           const bool tma = make_load_map(g, d_pixels, &tm);
           launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, ctx->d_flat, tma ? &tm : nullptr, s); }
         { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, (uint64_t)n * g.nb, ctx->d_table, ctx->d_bits, s); }
-        bool fused;
-        { KernelTimer t(ctx, FLIC_K_SLOTS, s);
-          fused = launch_slots(g, ctx->d_bits, ctx->d_dirE, ctx->d_slot_status, ++ctx->slot_epoch, cap_words, ctx->d_err,
-                               (uint32_t *)d_streams, (unsigned long long *)d_offsets, ctx->slots_max_grid, s); }
-        if (!fused) {  // headers and directories depend on the slots only: before k_pack, off its tail
+        // Slots and ONE_STREAM: every block's position follows from its histogram and code lengths (k_slots), and the
+        // headers and directories from the positions — before k_pack, off its tail.  EXACT: positions exist only once the
+        // blocks are packed (k_pack looks back over the packed sizes), so k_finalize comes last and there is no k_slots.
+        bool fused = false;
+        if (!exact) {
+            { KernelTimer t(ctx, FLIC_K_SLOTS, s);
+              fused = launch_slots(g, ctx->d_bits, ctx->d_dirE, ctx->d_slot_status, ++ctx->slot_epoch, cap_words, ctx->d_err,
+                                   (uint32_t *)d_streams, (unsigned long long *)d_offsets, ctx->slots_max_grid, s); }
+            if (!fused) {
+                KernelTimer t(ctx, FLIC_K_FINALIZE, s);
+                launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s);
+            }
+        }
+        { KernelTimer t(ctx, FLIC_K_PACK, s);
+          launch_pack(ctx->d_resid, g, ctx->d_table, ctx->d_flat, (uint32_t *)d_streams, cap_words, ctx->d_dirE, ctx->d_err,
+                      ctx->d_status, ctx->d_ticket, ctx->ticket_base, ctx->fused_epoch, s); }
+        if (exact) {
+            ctx->ticket_base += (uint64_t)n * g.nb;  // one ticket per CTA, one CTA per block
             KernelTimer t(ctx, FLIC_K_FINALIZE, s);
             launch_finalize(g, ctx->d_dirE, (uint32_t *)d_streams, cap_words, (unsigned long long *)d_offsets, ctx->d_err, s);
         }
-        { KernelTimer t(ctx, FLIC_K_PACK, s);
-          launch_pack(ctx->d_resid, g, ctx->d_table, ctx->d_flat, (uint32_t *)d_streams, cap_words, ctx->d_dirE, ctx->d_err, s); }
-        ctx->launches += fused ? 4 : 5;
+        ctx->launches += exact ? 4 : (fused ? 4 : 5);
     }
     CU(cudaEventRecord(ctx->ev_ws, s));
     ctx->ws_stream = s; ctx->ws_used = true;

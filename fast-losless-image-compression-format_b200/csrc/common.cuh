@@ -194,8 +194,10 @@ int slots_max_resident_ctas();  // how many k_slots CTAs this device keeps resid
 bool launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_dirE, unsigned long long *d_status,
                   uint32_t epoch, uint64_t capacity_words, uint32_t *d_err, uint32_t *d_streams,
                   unsigned long long *d_offsets, int max_grid, cudaStream_t s);
+// d_status / d_ticket / ticket_base / epoch: look-back state, used by FLIC_FLAG_EXACT only (the launch draws n * nb tickets)
 void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, const uint2 *d_flat, uint32_t *d_streams,
-                 uint64_t capacity_words, const unsigned long long *d_dirE, uint32_t *d_err, cudaStream_t s);
+                 uint64_t capacity_words, unsigned long long *d_dirE, uint32_t *d_err, unsigned long long *d_status,
+                 unsigned long long *d_ticket, unsigned long long ticket_base, uint32_t epoch, cudaStream_t s);
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,
                      uint64_t capacity_words, unsigned long long *d_offsets, uint32_t *d_err,
                      cudaStream_t s);

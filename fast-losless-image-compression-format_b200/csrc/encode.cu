@@ -591,7 +591,9 @@ __global__ void __launch_bounds__(256) k_finalize(Geo g, const unsigned long lon
 // contiguous run of blocks, publish the run's sum tagged with this launch's epoch (no memset between
 // launches), sum their predecessors' published values, then scan their own run.
 constexpr int kSlotThreads = 1024;
-__device__ __forceinline__ uint32_t slot_words(uint32_t code_bits, uint32_t b, uint32_t last_row_first, uint32_t last_bha) {
+// one: FLIC_FLAG_ONE_STREAM — the block is its header and ONE bit stream, whose exact length the histogram gives.
+__device__ __forceinline__ uint32_t slot_words(uint32_t code_bits, uint32_t b, uint32_t last_row_first, uint32_t last_bha, bool one) {
+    if (one) return (uint32_t)kBlkHdrWords1 + ((code_bits + 31u) >> 5);
     return (uint32_t)kBlkHdrWords + (code_bits >> 5) + (code_bits ? (b >= last_row_first ? last_bha : (uint32_t)kBH) : 0u);
 }
 __global__ void __launch_bounds__(kSlotThreads) k_slots(Geo g, const uint32_t *__restrict__ bits,
@@ -605,10 +607,11 @@ __global__ void __launch_bounds__(kSlotThreads) k_slots(Geo g, const uint32_t *_
     const uint64_t total = (uint64_t)g.n * g.nb;
     const uint64_t lo = (uint64_t)blockIdx.x * per, hi = min(total, lo + per);
     const uint32_t last_row_first = (g.nby - 1) * g.nbx, last_bha = g.h - (g.nby - 1) * kBH;
+    const bool one = one_stream(g.flags);
     // pass 1: the run's sum
     uint32_t sum = 0;
     for (uint64_t gb = lo + tid; gb < hi; gb += kSlotThreads)
-        sum += slot_words(__ldg(bits + gb), (uint32_t)(gb % g.nb), last_row_first, last_bha);
+        sum += slot_words(__ldg(bits + gb), (uint32_t)(gb % g.nb), last_row_first, last_bha, one);
     sum = __reduce_add_sync(0xFFFFFFFFu, sum);
     if (lane == 0) wsum[warp] = sum;
     __syncthreads();
@@ -638,7 +641,7 @@ __global__ void __launch_bounds__(kSlotThreads) k_slots(Geo g, const uint32_t *_
     unsigned long long carry = s_excl;
     for (uint64_t base = lo; base < hi; base += kSlotThreads) {
         const uint64_t gb = base + tid;
-        const uint32_t v = gb < hi ? slot_words(__ldg(bits + gb), (uint32_t)(gb % g.nb), last_row_first, last_bha) : 0u;
+        const uint32_t v = gb < hi ? slot_words(__ldg(bits + gb), (uint32_t)(gb % g.nb), last_row_first, last_bha, one) : 0u;
         const uint32_t incl = warp_incl_scan(v, lane);
         __syncthreads();
         if (lane == 31) wsum[warp] = incl;
@@ -683,6 +686,101 @@ bool launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_di
     k_slots<<<grid, kSlotThreads, 0, s>>>(g, d_bits, d_dirE, (uint32_t)per, epoch, d_status, capacity_words, d_err, d_streams,
                                           d_offsets);
     return grid == 1;
+}
+
+// ------------------------------------------------------- decoupled look-back (k_pack EXACT, k_encode)
+// look-back status word: epoch (22 bits) | flag (2) | value (40 bits, words)
+constexpr unsigned long long kStA = 1ull << 40, kStP = 2ull << 40, kStVal = (1ull << 40) - 1;
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// One warp: the exclusive prefix of the sizes of all blocks before gb (gb > 0), 32 predecessors per step.  A predecessor
+// publishes its own size (kStA) as soon as it knows it and its inclusive prefix (kStP) once it has looked back itself.
+// Block indices are handed out in order (a ticket counter), so every predecessor is running or done: the wait ends.
+__device__ __forceinline__ unsigned long long lookback_excl(const unsigned long long *status, uint64_t gb, uint32_t epoch, int lane) {
+    // One window of 32 per step.  Requesting four windows at once (128 status words in flight per L2 round trip) was
+    // measured SLOWER (k_pack EXACT 1.67 -> 1.84 ms on the 4K RGBA batch): the wait is for the predecessors to finish
+    // packing, not for the loads, and the extra polls only add traffic.
+    constexpr int kLbK = 1;
+    unsigned long long excl = 0;
+    long long j0 = (long long)gb - 1 - lane;
+    for (;;) {
+        unsigned long long v[kLbK];
+#pragma unroll
+        for (int k = 0; k < kLbK; ++k) v[k] = j0 - 32 * k >= 0 ? ld_status(status + (j0 - 32 * k)) : 0ull;
+        unsigned long long c = 0;
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < kLbK; ++k) {
+            const long long j = j0 - 32 * k;
+            if (!done) {
+                if (j >= 0) {
+                    // a predecessor that has not published yet is still working on its block: sleep instead of spinning,
+                    // the issue slots are what the other CTAs of the SM are short of
+                    while ((v[k] >> 42) != epoch || (v[k] & (kStA | kStP)) == 0) { __nanosleep(64); v[k] = ld_status(status + j); }
+                }
+                const uint32_t pmask = __ballot_sync(0xFFFFFFFFu, j >= 0 && (v[k] & kStP) != 0);
+                const int stop = pmask ? __ffs(pmask) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
+                if (j >= 0 && lane <= stop) c += v[k] & kStVal;
+                if (pmask || j - (31 - lane) <= 0) done = true;  // found a prefix, or the window reached block 0 (uniform: lane 31's j)
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const uint32_t lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)c, d), hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(c >> 32), d);
+            c += ((unsigned long long)hi << 32) | lo;
+        }
+        excl += c;
+        if (done) break;
+        j0 -= 32 * kLbK;
+    }
+    return excl;
+}
+
+// ------------------------------------------------- ONE_STREAM copy-out (k_pack kLayOne, k_encode)
+// FLP0 §8: the rows back to back, bit-exactly, into out[0, nw).  Row r is staged MSB-first from word 0 of its staging
+// row (zero past its last bit, one word beyond included) and starts at stream bit
+// rbit0[r].  One warp per row: every lane shifts by the same amount, interior words of a row go straight out
+// (coalesced); the first and the last word of a row may be shared with its neighbours, so they are parked as
+// (word index, value) pairs — two per row, in stream order — and warp 0 ORs the runs of equal index together at the end.
+struct EdgeWords { uint32_t idx[2 * kBH], val[2 * kBH]; };
+__device__ __forceinline__ void concat_rows(const uint32_t *stage0 /* row 0, word 0 */, int pitch, const uint32_t *rbit0, EdgeWords &e,
+                                            uint32_t *out, uint32_t nw, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < kBH; r += kEncWarps) {
+        const uint32_t s0 = rbit0[r], s1 = rbit0[r + 1], sh = s0 & 31u, f = s0 >> 5;
+        const uint32_t *src = stage0 + r * pitch;
+        if (s1 == s0) {  // no bits: a zero contribution that keeps the neighbours' shared word adjacent in the list
+            if (lane < 2) { e.idx[2 * r + lane] = f; e.val[2 * r + lane] = 0u; }
+            continue;
+        }
+        const uint32_t l = (s1 - 1u) >> 5, nrw = l - f + 1u;
+        for (uint32_t k = lane; k < nrw; k += 32) {
+            const uint32_t v = __funnelshift_r(src[k], k ? src[k - 1] : 0u, sh);  // (src[k-1] << (32 - sh)) | (src[k] >> sh)
+            if (k == 0) { e.idx[2 * r] = f; e.val[2 * r] = v; }
+            else if (k == nrw - 1u) { e.idx[2 * r + 1] = l; e.val[2 * r + 1] = v; }
+            else out[f + k] = v;
+        }
+        if (nrw == 1u && lane == 0) { e.idx[2 * r + 1] = l; e.val[2 * r + 1] = 0u; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            const uint32_t w = e.idx[i];
+            if ((i == 0 || e.idx[i - 1] != w) && w < nw) {  // head of a run of equal word indices
+                uint32_t v = e.val[i];
+                for (int t = i + 1; t < 2 * kBH && e.idx[t] == w; ++t) v |= e.val[t];
+                out[w] = v;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------- k_pack
@@ -748,25 +846,42 @@ __device__ __forceinline__ uint32_t quad3(uint32_t w, const uint32_t *tab, const
     return __umulhi(e0 + e1 + e2, pm.m8);
 }
 
-template <int C>
+// Layouts (FLP0 §3.8): where a block goes and what its payload looks like.
+//   kLaySlots : position and size from k_slots (histogram x code lengths); interleaved row sub-streams; slack zeroed
+//   kLayOne   : FLIC_FLAG_ONE_STREAM — position from k_slots too (the block's size is exactly header + ceil(code bits / 32));
+//               the rows leave concatenated bit-exactly into ONE stream
+//   kLayExact : FLIC_FLAG_EXACT — the block occupies exactly the words it packed, so its position is known only after the
+//               packing: blocks are claimed in order (a ticket), publish their size and look back over their predecessors'
+enum { kLaySlots = 0, kLayOne = 1, kLayExact = 2 };
+
+template <int C, int LAY>
 __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restrict__ resid, Geo g,
                                                       const uint16_t *__restrict__ table,
                                                       const uint2 *__restrict__ flat,
                                                       uint32_t *__restrict__ streams, uint64_t capacity_words,
-                                                      const unsigned long long *__restrict__ dirE,
-                                                      uint32_t *err, PackMul pm) {
-    __shared__ __align__(16) uint32_t stage[kBH * kStagePitch];
+                                                      unsigned long long *dirE,
+                                                      uint32_t *err, PackMul pm, unsigned long long *status,
+                                                      unsigned long long *ticket, unsigned long long ticket_base, uint32_t epoch) {
+    __shared__ __align__(16) uint32_t stage[kBH * kStagePitch + 4];  // + 4: kLayOne reads one word past a row's last
     __shared__ uint32_t tab[256];  // code | len << 24; 0 for a sole symbol (no bits)
     __shared__ uint8_t nib[256];
-    __shared__ uint32_t rwc[kBH], rowoff[kBH];
+    __shared__ uint32_t rwc[kBH], rowoff[kBH], rbit0[LAY == kLayOne ? kBH + 1 : 1];
+    __shared__ EdgeWords edges;  // (kLayOne only; 512 bytes)
     __shared__ uint32_t s_minw, s_used;
+    __shared__ unsigned long long s_excl;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint64_t gb = blockIdx.x;
+    uint64_t gb = blockIdx.x;
+    if (LAY == kLayExact) {  // blocks in ticket order: whoever holds block gb knows that every block before it has started
+        if (tid == 0) s_excl = atomicAdd(ticket, 1ull) - ticket_base;
+        __syncthreads();
+        gb = s_excl;
+        __syncthreads();
+    }
     const BlockPos p = block_pos(g, gb);
     {
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *s4 = reinterpret_cast<uint4 *>(stage);
-        for (int i = tid; i < kBH * kStagePitch / 4; i += kEncThreads) s4[i] = z;
+        for (int i = tid; i < (kBH * kStagePitch + 4) / 4; i += kEncThreads) s4[i] = z;
     }
 
     {
@@ -829,7 +944,10 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
                 for (int j = 0; j < C; ++j) { ql[j] = quad_of<false, -1>(cur[j], 4 * j, nv, skip[j], tab, pm, qlo[j], qhi[j]); nbits += ql[j]; }
             }
             const uint32_t incl = warp_incl_scan(nbits, lane);
-            if (lane == 31) rwc[r] = (incl + 31u) >> 5;
+            if (lane == 31) {
+                rwc[r] = (incl + 31u) >> 5;
+                if (LAY == kLayOne) rbit0[r] = incl;
+            }
             // nb = -(bit address in shared memory of the lane's next free bit); its low 5 bits are the shift
             uint32_t nb = 0u - (8u * (sstage + 4u * (uint32_t)(r * kStagePitch + kStagePad)) + (incl - nbits));
             if (kNarrow) {
@@ -864,27 +982,58 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     else pack_rows(std::false_type{});
     __syncthreads();
 
-    // FLP0 §7: the block's slot (position and size) was fixed by k_slots from the histogram and the code
-    // lengths, so there is nothing to wait for: no ordering between blocks, no look-back.
-    const unsigned long long excl = dirE[gb];
-    const uint32_t slot = (uint32_t)(dirE[gb + 1] - excl);
-    const unsigned long long base = (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + excl;
+    constexpr int hdrw = LAY == kLayOne ? kBlkHdrWords1 : kBlkHdrWords;
+    unsigned long long excl = 0;
+    uint32_t slot = 0;
+    if (LAY != kLayExact) {
+        // FLP0 §7: the block's slot (position and size) was fixed by k_slots from the histogram and the code
+        // lengths, so there is nothing to wait for: no ordering between blocks, no look-back.
+        excl = dirE[gb];
+        slot = (uint32_t)(dirE[gb + 1] - excl);
+    }
     if (warp == 0) {
-        const uint32_t wcount = rwc[lane];
-        const uint32_t incl = warp_incl_scan(wcount, lane);
-        rowoff[lane] = incl - wcount;
-        uint32_t mn = lane < (int)p.bha ? wcount : 0xFFFFFFFFu;  // FLP0 §6: interleave depth
+        uint32_t used, mn = 0;
+        if (LAY == kLayOne) {  // first bit of every row in the block's one stream
+            const uint32_t rb = rbit0[lane];
+            const uint32_t bincl = warp_incl_scan(rb, lane);
+            __syncwarp();
+            rbit0[lane] = bincl - rb;
+            if (lane == 31) rbit0[kBH] = bincl;
+            used = (uint32_t)hdrw + ((__shfl_sync(0xFFFFFFFFu, bincl, 31) + 31u) >> 5);
+        } else {
+            const uint32_t wcount = rwc[lane];
+            const uint32_t incl = warp_incl_scan(wcount, lane);
+            rowoff[lane] = incl - wcount;
+            mn = lane < (int)p.bha ? wcount : 0xFFFFFFFFu;  // FLP0 §6: interleave depth
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
-        const uint32_t used = kBlkHdrWords + __shfl_sync(0xFFFFFFFFu, incl, 31);
+            for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+            used = (uint32_t)hdrw + __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (LAY == kLayExact) {
+            const unsigned long long ep = (unsigned long long)epoch << 42;
+            slot = used;
+            if (gb > 0) {
+                if (lane == 0) st_status(status + gb, ep | kStA | slot);
+                excl = lookback_excl(status, gb, epoch, lane);
+            }
+            if (lane == 0) {
+                st_status(status + gb, ep | kStP | ((excl + slot) & kStVal));
+                dirE[gb] = excl;
+                if (gb + 1 == (uint64_t)g.n * g.nb) dirE[gb + 1] = excl + slot;
+                s_excl = excl;
+            }
+        }
         if (lane == 0) {
             s_minw = mn;
             s_used = used;
-            if (used > slot) atomicOr(err, kErrSlot);  // cannot happen: rows pad by less than a word each
+            // cannot happen: a slot covers the rows' padding (slots), is the stream's exact length (one stream)
+            if (used > slot || (LAY == kLayOne && used != slot)) atomicOr(err, kErrSlot);
         }
     }
     __syncthreads();
-    if (s_used > slot) return;
+    if (LAY == kLayExact) { excl = s_excl; slot = s_used; }
+    if (s_used > slot || (LAY == kLayOne && s_used != slot)) return;
+    const unsigned long long base = (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + excl;
     if (base + slot > capacity_words) {
         if (tid == 0) atomicOr(err, kErrCapacity);
         return;
@@ -896,14 +1045,18 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
 #pragma unroll
         for (int k = 0; k < 8; ++k) v |= (uint32_t)nib[8 * lane + k] << (4 * k);
         out[lane] = v;
-    } else if (warp == 1 && lane < kBH / 2) {
+    } else if (LAY != kLayOne && warp == 1 && lane < kBH / 2) {
         out[32 + lane] = rwc[2 * lane] | (rwc[2 * lane + 1] << 16);
     } else if (warp == 2 && lane < 2) {
-        out[kFlatWord + lane] = lane ? fl.y : fl.x;
+        out[hdrw - 2 + lane] = lane ? fl.y : fl.x;
+    }
+    out += hdrw;
+    if (LAY == kLayOne) {
+        concat_rows(stage + kStagePad, kStagePitch, rbit0, edges, out, slot - (uint32_t)hdrw, tid);
+        return;
     }
     // interleaved region: word k of row r lands at k*bha + r (coalesced stores, conflict-free column reads)
     const uint32_t minw = s_minw, bha = p.bha, inter = minw * bha;
-    out += kBlkHdrWords;
     if (bha == (uint32_t)kBH) {  // thread = (k = warp, r = lane): i = k*32 + r = tid, then k += 8 per step
         const uint32_t *src = stage + lane * kStagePitch + kStagePad + warp;
         uint32_t *dst = out + tid;
@@ -926,12 +1079,22 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     }
 }
 
+// status / ticket / ticket_base / epoch: the look-back state of the EXACT layout (shared with the fused encoder); the
+// grid is exactly one CTA per block, so the launch consumes n * nb tickets.
 void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, const uint2 *d_flat, uint32_t *d_streams,
-                 uint64_t capacity_words, const unsigned long long *d_dirE, uint32_t *d_err, cudaStream_t s) {
+                 uint64_t capacity_words, unsigned long long *d_dirE, uint32_t *d_err, unsigned long long *d_status,
+                 unsigned long long *d_ticket, unsigned long long ticket_base, uint32_t epoch, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
     const PackMul pm = {1u << 8, 1u << 10, 1u << 18, 1u << 26};
-#define FLIC_PACK(C) \
-    k_pack<C><<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_flat, d_streams, capacity_words, d_dirE, d_err, pm)
+#define FLIC_PACK2(C, LAY) \
+    k_pack<C, LAY><<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_flat, d_streams, capacity_words, d_dirE, d_err, pm, \
+                                                           d_status, d_ticket, ticket_base, epoch)
+#define FLIC_PACK(C)                                                          \
+    do {                                                                      \
+        if (g.flags & FLIC_FLAG_EXACT) FLIC_PACK2(C, kLayExact);              \
+        else if (g.flags & FLIC_FLAG_ONE_STREAM) FLIC_PACK2(C, kLayOne);      \
+        else FLIC_PACK2(C, kLaySlots);                                        \
+    } while (0)
     switch (g.c) {
         case 1: FLIC_PACK(1); break;
         case 2: FLIC_PACK(2); break;
@@ -939,6 +1102,7 @@ void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table,
         default: FLIC_PACK(4); break;
     }
 #undef FLIC_PACK
+#undef FLIC_PACK2
 }
 
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,
@@ -1130,20 +1294,11 @@ void launch_tables_cta(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_tab
     k_tables_cta<<<(unsigned)nblocks, kEncThreads, 0, s>>>(d_hist, d_table, d_bits);
 }
 
-// look-back status word: epoch (22 bits) | flag (2) | value (40 bits, words)
-constexpr unsigned long long kStA = 1ull << 40, kStP = 2ull << 40, kStVal = (1ull << 40) - 1;
-__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 struct FusedSmem {
     union { uint32_t sh[kEncWarps][256]; TabScratch t; } u;  // first: the sub-histograms must be 1 KB-aligned (hist_inc)
     uint32_t tile[kBH * kStagePitch];  // per row: residual words (word j of lane L at j*32 + L), then the packed row
+    uint32_t tile_guard[4];            // ONE_STREAM clears and reads one word past a row: the last row's may be the tile's last
+    EdgeWords edges;                   // ONE_STREAM copy-out
     uint32_t tab[256];
     uint8_t nib[256];
     uint32_t rwc[kBH], rowoff[kBH], rbit0[kBH + 1];  // words per row, word offset of each row's tail, first bit of each row
@@ -1371,26 +1526,7 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
             unsigned long long excl = 0;
             if (gb > 0) {
                 if (exact && lane == 0) st_status(status + gb, ep | kStA | size);
-                long long j = (long long)gb - 1 - lane;
-                for (;;) {
-                    unsigned long long v = 0;
-                    if (j >= 0) {
-                        // a predecessor that has not published yet is still building its table (or packing, with EXACT):
-                        // sleep instead of spinning, the issue slots are what the other CTAs of the SM are short of
-                        while (v = ld_status(status + j), (v >> 42) != epoch || (v & (kStA | kStP)) == 0) __nanosleep(64);
-                    }
-                    const uint32_t pmask = __ballot_sync(0xFFFFFFFFu, j >= 0 && (v & kStP) != 0);
-                    const int stop = pmask ? __ffs(pmask) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
-                    unsigned long long c = (j >= 0 && lane <= stop) ? (v & kStVal) : 0ull;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) {
-                        const uint32_t lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)c, d), hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(c >> 32), d);
-                        c += ((unsigned long long)hi << 32) | lo;
-                    }
-                    excl += c;
-                    if (pmask || j - (31 - lane) <= 0) break;  // found a prefix, or the window reached block 0 (uniform: lane 31's j)
-                    j -= 32;
-                }
+                excl = lookback_excl(status, gb, epoch, lane);
             }
             if (lane == 0) {
                 st_status(status + gb, ep | kStP | ((excl + size) & kStVal));
@@ -1427,29 +1563,7 @@ k_encode(const uint8_t *__restrict__ pixels, Geo g, uint32_t *__restrict__ strea
         }
         out += hdrw;
         if (one) {
-            // FLP0 §8: the rows back to back, bit-exactly.  Output word m holds stream bits [32m, 32m + 32): find the
-            // row that bit 32m falls in, then OR in every row that overlaps the word (staged rows are zero past
-            // their last bit, one word beyond included).
-            const uint32_t nw = size - (uint32_t)kBlkHdrWords1;
-            for (uint32_t m = tid; m < nw; m += kEncThreads) {
-                const uint32_t b0 = 32u * m;
-                int r = 0;
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1) r += (r + s < kBH && sm.rbit0[r + s] <= b0) ? s : 0;
-                uint32_t acc = 0;
-                for (; r < kBH && sm.rbit0[r] < b0 + 32u; ++r) {
-                    if (sm.rbit0[r + 1] <= b0 || sm.rbit0[r + 1] == sm.rbit0[r]) continue;  // an empty row
-                    const uint32_t *src = sm.tile + r * kStagePitch + kStagePad;
-                    const uint32_t s0 = sm.rbit0[r];
-                    if (s0 <= b0) {
-                        const uint32_t rel = b0 - s0;
-                        acc |= __funnelshift_l(src[(rel >> 5) + 1], src[rel >> 5], rel & 31u);
-                    } else {
-                        acc |= src[0] >> (s0 - b0);
-                    }
-                }
-                out[m] = acc;
-            }
+            concat_rows(sm.tile + kStagePad, kStagePitch, sm.rbit0, sm.edges, out, size - (uint32_t)kBlkHdrWords1, tid);
             continue;
         }
         for (uint32_t i = used + tid; i < size; i += kEncThreads) (out - hdrw)[i] = 0u;  // slack of the slot

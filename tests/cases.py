@@ -28,6 +28,29 @@ def skewed(w, h, c, seed):
     return (np.cumsum(steps, axis=1) & 255).astype(np.uint8)
 
 
+def from_residuals(res):
+    """The image whose FLP0 residuals (left predictor; column 0 from the pixel above; no colour transform) are `res`."""
+    res = res.astype(np.int64)
+    col0 = np.cumsum(res[:, 0, :], axis=0)                      # column 0: running sum down the rows
+    rows = np.cumsum(res[:, 1:, :], axis=1) + col0[:, None, :]  # then along each row
+    return (np.concatenate([col0[:, None, :], rows], axis=1) & 255).astype(np.uint8)
+
+
+def max_len_row(seed, c=4):
+    """One block whose LAST row is made of maximum-length codes only (128*c symbols x 10 bits = the 160-word worst case
+    of a row sub-stream when c == 4): six frequent symbols in rows 0..30, 250 rare ones in row 31."""
+    rng = np.random.default_rng(seed)
+    n = 31 * 128 * c
+    counts = np.array([0.504, 0.252, 0.126, 0.063, 0.0315]) * n
+    counts = counts.astype(np.int64)
+    top = np.repeat(np.arange(6), list(counts) + [n - counts.sum()])
+    rng.shuffle(top)
+    rare = np.concatenate([np.arange(6, 256), rng.integers(6, 256, 128 * c)])[:128 * c] if 128 * c >= 250 else np.arange(6, 6 + 128 * c)
+    rng.shuffle(rare)
+    res = np.concatenate([top, rare]).reshape(32, 128, c)
+    return from_residuals(res)
+
+
 def with_const(img, **chans):
     """Force channels to constants (flat channels, FLP0 §2b); e.g. with_const(img, c1=77)."""
     img = img.copy()
@@ -69,4 +92,7 @@ SMALL = [
     ("const_a_77x45x2", lambda: with_const(gradient(77, 45, 2, 17), c1=255)),
     ("two_flat_300x70x4", lambda: with_const(gradient(300, 70, 4, 18), c2=9, c3=200)),
     ("partly_flat_384x64x4", lambda: np.concatenate([gradient(128, 64, 4, 19), noise(256, 64, 4, 20)], axis=1)),
+    # the last row of the block is 160 words long (every symbol a 10-bit code): the staging tile's very last word
+    ("max_len_row_128x32x4", lambda: max_len_row(21, 4)),
+    ("max_len_row_128x32x3", lambda: max_len_row(22, 3)),
 ]

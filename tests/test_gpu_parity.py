@@ -62,8 +62,10 @@ def test_stage_histograms_and_tables(codec, oracle, encoder, name, build, flags)
 
 
 @pytest.mark.parametrize("name,build", cases.SMALL, ids=[n for n, _ in cases.SMALL])
-@pytest.mark.parametrize("flags", [0x01, 0x11])
+@pytest.mark.parametrize("flags", cases.ALL_FLAGS)
 def test_staged_encoder_bytes(codec, oracle, name, build, flags):
+    """The staged pipeline in every layout: slots, ONE_STREAM (k_slots with exact sizes, bit-exact row concatenation in
+    k_pack) and EXACT (k_pack places blocks with a look-back over the packed sizes)."""
     codec.set_encoder("staged")
     try:
         img = build()
@@ -371,15 +373,30 @@ def test_c4_strip_roundtrip(codec):
 
 # ---- round 2: layouts, fused encoder, async host API, device splice ----
 @pytest.mark.parametrize("flags", [0x21, 0x41])
-def test_layout_modes_full_size(codec, oracle, flags):
-    """ONE_STREAM (self-synchronising decoder) and EXACT (look-back over packed sizes) on full-size inputs:
-    a 4K RGBA gradient image, a 4K RGBA noise image (code lengths 7-9: the slowest to synchronise) and a
-    1080p RGB image, each byte-compared with the model and decoded back."""
+def test_layout_modes_full_size(codec, oracle, encoder, flags):
+    """ONE_STREAM (self-synchronising decoder) and EXACT (look-back over packed sizes) on full-size inputs, through the
+    fused and the staged encoder: a 4K RGBA gradient image, a 4K RGBA noise image (code lengths 7-9: the slowest to
+    synchronise) and a 1080p RGB image, each byte-compared with the model and decoded back."""
     import flic_b200 as flic
     for imgs in (flic.workloads.make_batch("C2"), flic.workloads.make_batch("C5", n=1), flic.workloads.make_batch("C3", n=2)):
         streams, off = _roundtrip_device(codec, imgs, flags)
         got = streams[: int(off[1])].cpu().numpy()
         assert np.array_equal(got, oracle.encode(imgs[0], flags))
+
+
+def test_lookback_state_is_shared_between_the_encoders(codec, oracle):
+    """The fused kernel and the staged EXACT packer draw tickets from one counter and tag one status array with one epoch:
+    alternate them, launch after launch, on a batch of many blocks (24 images x 3 x 9 blocks) and compare every image."""
+    imgs = np.stack([cases.gradient(300, 270, 3, 100 + s) if s % 3 else cases.noise(300, 270, 3, 100 + s) for s in range(24)])
+    want = {fl: [oracle.encode(im, fl) for im in imgs] for fl in (0x41, 0x21, 0x01)}
+    for rep in range(3):
+        for enc in ("staged", "fused"):
+            codec.set_encoder(enc)
+            for fl in (0x41, 0x21, 0x01):
+                streams, off = _roundtrip_device(codec, imgs, fl)
+                got = streams[: int(off[-1])].cpu().numpy()
+                for i in range(len(imgs)):
+                    assert np.array_equal(got[int(off[i]): int(off[i + 1])], want[fl][i]), (rep, enc, hex(fl), i)
 
 
 def test_one_stream_pathological_codes(codec, oracle):
