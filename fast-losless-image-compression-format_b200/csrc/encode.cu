@@ -78,7 +78,8 @@ __device__ __forceinline__ uint32_t word_channel_bits(uint32_t mask, int j) {
 template <int C, bool SG, bool kTma>
 __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__restrict__ pixels, Geo g,
                                                             uint16_t *__restrict__ hist, uint32_t *__restrict__ resid,
-                                                            uint2 *__restrict__ flat, const __grid_constant__ CUtensorMap tmap) {
+                                                            uint2 *__restrict__ flat, const __grid_constant__ CUtensorMap tmap,
+                                                            int grid3) {
     constexpr int kSubHist = SubHist<C>::k;
     static_assert(kSubHist >= 1 && kSubHist <= kEncWarps && (kSubHist & (kSubHist - 1)) == 0, "power of two");
     __shared__ __align__(1024) uint32_t sh[kSubHist][256];  // 1 KB-aligned rows: hist_inc() ORs the offset into the base
@@ -86,8 +87,8 @@ __global__ void __launch_bounds__(kEncThreads, 6) k_histograms(const uint8_t *__
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t s_or[C], s_first;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint64_t gb = blockIdx.x;
-    const BlockPos p = block_pos(g, gb);
+    uint64_t gb;
+    const BlockPos p = block_pos_cta(g, grid3 != 0, gb);
     if (kTma && tid == 0) {
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar), dst = (uint32_t)__cvta_generic_to_shared(ptile);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
@@ -264,13 +265,14 @@ void launch_histograms(const uint8_t *d_pixels, const Geo &g, uint16_t *d_hist, 
                        const void *tensor_map, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
     const bool sg = (g.flags & FLIC_FLAG_SUBGREEN) && g.c >= 3;
-    const unsigned grid = (unsigned)total;
+    const bool g3 = grid3_ok(g);
+    const dim3 grid = g3 ? dim3(g.nbx, g.nby, g.n) : dim3((unsigned)total);
     CUtensorMap tm;
     if (tensor_map) memcpy(&tm, tensor_map, sizeof tm); else memset(&tm, 0, sizeof tm);
 #define FLIC_HIST(C, SG)                                                                                            \
     do {                                                                                                            \
-        if (tensor_map) k_histograms<C, SG, true><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid, d_flat, tm);  \
-        else k_histograms<C, SG, false><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid, d_flat, tm);            \
+        if (tensor_map) k_histograms<C, SG, true><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid, d_flat, tm, g3);  \
+        else k_histograms<C, SG, false><<<grid, kEncThreads, 0, s>>>(d_pixels, g, d_hist, d_resid, d_flat, tm, g3);            \
     } while (0)
     switch (g.c) {
         case 1: FLIC_HIST(1, false); break;
@@ -861,7 +863,8 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
                                                       uint32_t *__restrict__ streams, uint64_t capacity_words,
                                                       unsigned long long *dirE,
                                                       uint32_t *err, PackMul pm, unsigned long long *status,
-                                                      unsigned long long *ticket, unsigned long long ticket_base, uint32_t epoch) {
+                                                      unsigned long long *ticket, unsigned long long ticket_base, uint32_t epoch,
+                                                      int grid3) {
     __shared__ __align__(16) uint32_t stage[kBH * kStagePitch + 4];  // + 4: kLayOne reads one word past a row's last
     __shared__ uint32_t tab[256];  // code | len << 24; 0 for a sole symbol (no bits)
     __shared__ uint8_t nib[256];
@@ -870,14 +873,17 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     __shared__ uint32_t s_minw, s_used;
     __shared__ unsigned long long s_excl;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t gb = blockIdx.x;
+    uint64_t gb;
+    BlockPos p;
     if (LAY == kLayExact) {  // blocks in ticket order: whoever holds block gb knows that every block before it has started
         if (tid == 0) s_excl = atomicAdd(ticket, 1ull) - ticket_base;
         __syncthreads();
         gb = s_excl;
         __syncthreads();
+        p = block_pos(g, gb);
+    } else {
+        p = block_pos_cta(g, grid3 != 0, gb);
     }
-    const BlockPos p = block_pos(g, gb);
     {
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *s4 = reinterpret_cast<uint4 *>(stage);
@@ -1086,9 +1092,11 @@ void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table,
                  unsigned long long *d_ticket, unsigned long long ticket_base, uint32_t epoch, cudaStream_t s) {
     uint64_t total = (uint64_t)g.n * g.nb;
     const PackMul pm = {1u << 8, 1u << 10, 1u << 18, 1u << 26};
+    const bool g3 = grid3_ok(g) && !(g.flags & FLIC_FLAG_EXACT);
+    const dim3 grid = g3 ? dim3(g.nbx, g.nby, g.n) : dim3((unsigned)total);
 #define FLIC_PACK2(C, LAY) \
-    k_pack<C, LAY><<<(unsigned)total, kEncThreads, 0, s>>>(d_resid, g, d_table, d_flat, d_streams, capacity_words, d_dirE, d_err, pm, \
-                                                           d_status, d_ticket, ticket_base, epoch)
+    k_pack<C, LAY><<<grid, kEncThreads, 0, s>>>(d_resid, g, d_table, d_flat, d_streams, capacity_words, d_dirE, d_err, pm, \
+                                                d_status, d_ticket, ticket_base, epoch, g3)
 #define FLIC_PACK(C)                                                          \
     do {                                                                      \
         if (g.flags & FLIC_FLAG_EXACT) FLIC_PACK2(C, kLayExact);              \
