@@ -412,12 +412,20 @@ __device__ __forceinline__ void sort_block(uint32_t *key, int n, uint16_t *Arow,
 
 // bits (optional): per block, the sum over symbols of count x code length — with the geometry that is
 // the block's slot size (FLP0 §7), so every block's output position is known before k_pack runs.
+// kTabWarps warps per CTA, each on its own run of blocks (they share nothing, there is no CTA barrier): one-warp CTAs ran
+// into the SM's limit of 32 resident CTAs and their launch overhead (17 warps resident on average of the 29 that fit).
+#ifndef FLIC_TAB_WARPS
+#define FLIC_TAB_WARPS 4
+#endif
+constexpr int kTabWarps = FLIC_TAB_WARPS;
 template <int BPW>
-__global__ void __launch_bounds__(32) k_tables(const uint16_t *__restrict__ hist, uint64_t nblocks,
+__global__ void __launch_bounds__(32 * kTabWarps) k_tables(const uint16_t *__restrict__ hist, uint64_t nblocks,
                                                uint16_t *__restrict__ table, uint32_t *__restrict__ bits, int bpw) {
-    __shared__ __align__(16) TabSmemT<BPW> s;
-    const int lane = threadIdx.x;
-    const uint64_t first = (uint64_t)blockIdx.x * bpw;
+    __shared__ __align__(16) TabSmemT<BPW> sw[kTabWarps];
+    const int lane = threadIdx.x & 31;
+    TabSmemT<BPW> &s = sw[threadIdx.x >> 5];
+    const uint64_t first = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * bpw;
+    if (first >= nblocks) return;
     const int cnt = (int)min((uint64_t)bpw, nblocks - first);
     int myn = 0;
 
@@ -526,15 +534,13 @@ __global__ void __launch_bounds__(32) k_tables(const uint16_t *__restrict__ hist
 
 void launch_tables(const uint16_t *d_hist, uint64_t nblocks, uint16_t *d_table, uint32_t *d_bits, cudaStream_t s) {
     // one block per warp for small jobs (latency: 512x512 RGB 27 -> 21 us), a few when that still fills the
-    // chip, up to `cap` blocks per warp (merge lanes busy) for large jobs.  FLIC_TAB_BPW: experiment switch.
-    static const int cap = [] { const char *e = getenv("FLIC_TAB_BPW"); const int v = e ? atoi(e) : kTabBpw; return v == 2 || v == 4 || v == 16 ? v : kTabBpw; }();
+    // chip, up to kTabBpw blocks per warp (merge lanes busy) for large jobs (measured: 2 / 4 / 16 per warp are slower)
     uint64_t want = nblocks / (148ull * 16);
-    int bpw = (int)(want < 1 ? 1 : (want > (uint64_t)cap ? cap : want));
-    unsigned grid = (unsigned)((nblocks + bpw - 1) / bpw);
-    if (cap == 2) k_tables<2><<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
-    else if (cap == 4) k_tables<4><<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
-    else if (cap == 16) k_tables<16><<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
-    else k_tables<kTabBpw><<<grid, 32, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
+    int bpw = (int)(want < 1 ? 1 : (want > (uint64_t)kTabBpw ? kTabBpw : want));
+    const uint64_t warps = (nblocks + bpw - 1) / bpw;
+    const int wpc = warps >= 148ull * 4 * kTabWarps ? kTabWarps : 1;  // small jobs: one warp per CTA spreads over more SMs
+    unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
+    k_tables<kTabBpw><<<grid, 32 * wpc, 0, s>>>(d_hist, nblocks, d_table, d_bits, bpw);
 }
 
 // ------------------------------------------------------------------ k_finalize
