@@ -699,21 +699,26 @@ bool launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_di
 // ------------------------------------------------------- decoupled look-back (k_pack EXACT, k_encode)
 // look-back status word: epoch (22 bits) | flag (2) | value (40 bits, words)
 constexpr unsigned long long kStA = 1ull << 40, kStP = 2ull << 40, kStVal = (1ull << 40) - 1;
+// A status word IS the message (epoch, flag and value travel in one 64-bit store; nothing else in memory is published
+// by it), so relaxed accesses at GPU scope are all the ordering it needs.  With st.release / ld.acquire every polling
+// load carried a fence: k_pack EXACT 1.67 ms instead of 1.48 on the 4K RGBA batch.
 __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 // One warp: the exclusive prefix of the sizes of all blocks before gb (gb > 0), 32 predecessors per step.  A predecessor
 // publishes its own size (kStA) as soon as it knows it and its inclusive prefix (kStP) once it has looked back itself.
 // Block indices are handed out in order (a ticket counter), so every predecessor is running or done: the wait ends.
 __device__ __forceinline__ unsigned long long lookback_excl(const unsigned long long *status, uint64_t gb, uint32_t epoch, int lane) {
-    // One window of 32 per step.  Requesting four windows at once (128 status words in flight per L2 round trip) was
-    // measured SLOWER (k_pack EXACT 1.67 -> 1.84 ms on the 4K RGBA batch): the wait is for the predecessors to finish
-    // packing, not for the loads, and the extra polls only add traffic.
+    // One window of 32 per step.  Everything wider was measured SLOWER on the 4K RGBA batch (k_pack EXACT, ms): four
+    // windows requested at once 1.67 -> 1.84; the whole CTA looking back (256 per step) 1.48 -> 1.72; a size pass that
+    // publishes the block's size before it is packed (so that nobody waits for a straggler) 1.48 -> 1.92.  What the
+    // look-back costs is status traffic and the instructions around it, not the depth of the search: with the positions
+    // of an identical earlier launch in place of the look-back the kernel takes 1.10 ms.
     constexpr int kLbK = 1;
     unsigned long long excl = 0;
     long long j0 = (long long)gb - 1 - lane;
@@ -877,23 +882,24 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     __shared__ uint32_t rwc[kBH], rowoff[kBH], rbit0[LAY == kLayOne ? kBH + 1 : 1];
     __shared__ EdgeWords edges;  // (kLayOne only; 512 bytes)
     __shared__ uint32_t s_minw, s_used;
-    __shared__ unsigned long long s_excl;
+    __shared__ unsigned long long s_excl, s_ticket;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t gb;
     BlockPos p;
-    if (LAY == kLayExact) {  // blocks in ticket order: whoever holds block gb knows that every block before it has started
-        if (tid == 0) s_excl = atomicAdd(ticket, 1ull) - ticket_base;
-        __syncthreads();
-        gb = s_excl;
-        __syncthreads();
-        p = block_pos(g, gb);
-    } else {
-        p = block_pos_cta(g, grid3 != 0, gb);
-    }
+    // blocks in ticket order (EXACT): whoever holds block gb knows that every block before it has started.  The ticket is
+    // drawn first and read after the zero-fill, which does not depend on it and covers the atomic's latency.
+    if (LAY == kLayExact && tid == 0) s_ticket = atomicAdd(ticket, 1ull) - ticket_base;
     {
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *s4 = reinterpret_cast<uint4 *>(stage);
         for (int i = tid; i < (kBH * kStagePitch + 4) / 4; i += kEncThreads) s4[i] = z;
+    }
+    if (LAY == kLayExact) {
+        __syncthreads();
+        gb = s_ticket;
+        p = block_pos(g, gb);
+    } else {
+        p = block_pos_cta(g, grid3 != 0, gb);
     }
 
     {
@@ -1022,14 +1028,13 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
             used = (uint32_t)hdrw + __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
         if (LAY == kLayExact) {
-            const unsigned long long ep = (unsigned long long)epoch << 42;
             slot = used;
             if (gb > 0) {
-                if (lane == 0) st_status(status + gb, ep | kStA | slot);
+                if (lane == 0) st_status(status + gb, ((unsigned long long)epoch << 42) | kStA | slot);
                 excl = lookback_excl(status, gb, epoch, lane);
             }
             if (lane == 0) {
-                st_status(status + gb, ep | kStP | ((excl + slot) & kStVal));
+                st_status(status + gb, ((unsigned long long)epoch << 42) | kStP | ((excl + slot) & kStVal));
                 dirE[gb] = excl;
                 if (gb + 1 == (uint64_t)g.n * g.nb) dirE[gb + 1] = excl + slot;
                 s_excl = excl;
@@ -1038,13 +1043,13 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
         if (lane == 0) {
             s_minw = mn;
             s_used = used;
-            // cannot happen: a slot covers the rows' padding (slots), is the stream's exact length (one stream)
-            if (used > slot || (LAY == kLayOne && used != slot)) atomicOr(err, kErrSlot);
+            // cannot happen: a slot covers the rows' padding (slots), is the stream's exact length (one stream, exact)
+            if (used > slot || (LAY != kLaySlots && used != slot)) atomicOr(err, kErrSlot);
         }
     }
     __syncthreads();
     if (LAY == kLayExact) { excl = s_excl; slot = s_used; }
-    if (s_used > slot || (LAY == kLayOne && s_used != slot)) return;
+    if (s_used > slot || (LAY != kLaySlots && s_used != slot)) return;
     const unsigned long long base = (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + excl;
     if (base + slot > capacity_words) {
         if (tid == 0) atomicOr(err, kErrCapacity);
