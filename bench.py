@@ -319,7 +319,20 @@ def c4_split(D, codec, args, K, W):
     _, w, h, c, _, seed = flic_b200.workloads.CONFIGS["C4"]
     if args.c4_height:
         h = args.c4_height
-    sc = flic_b200.sharding.ShardedImageCodec(codec, w, h, c, args.flags, D.dist, D.rank, D.world)
+    # peer memory when there is more than one rank and the box offers it (torch symmetric memory over NVLink): the pack
+    # kernels write straight into rank 0's buffer, nothing synchronises with the host.  Otherwise NCCL send/recv of parts.
+    sc, how, why = None, "nccl", None
+    if D.world > 1 and args.c4_mode != "nccl":
+        try:
+            sc = flic_b200.sharding.PeerImageCodec(codec, w, h, c, args.flags, D.dist, D.rank, D.world)
+            how = "peer"
+        except Exception as e:  # no symmetric memory on this box / torch build
+            why = "%s: %s" % (type(e).__name__, str(e)[:120])
+        agree = D.sum([1.0 if how == "peer" else 0.0])[0]
+        if agree != D.world:   # all ranks or none
+            sc, how = None, "nccl"
+    if sc is None:
+        sc = flic_b200.sharding.ShardedImageCodec(codec, w, h, c, args.flags, D.dist, D.rank, D.world)
     rows = synth_rows_cuda(torch, w, h, c, seed, sc.y0, sc.y1)[None]
     st = torch.cuda.current_stream().cuda_stream
     full = None
@@ -328,7 +341,10 @@ def c4_split(D, codec, args, K, W):
         got = sc.decode(full, st)
     codec.check(st)
     ok = bool(torch.equal(got, rows))
-    comp = int(full.numel()) if D.rank == 0 else 0
+    if how == "peer":
+        comp = sc.stream_bytes() if D.rank == 0 else 0
+    else:
+        comp = int(full.numel()) if D.rank == 0 else 0
     ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(K)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if rows.numel() < (512 << 20) else None
     launches0 = codec.launches
@@ -356,9 +372,14 @@ def c4_split(D, codec, args, K, W):
     return {"l2": l2, "value_GBps": round(raw / (tot * 1e-3) / 1e9, 2), "encode_GBps": round(raw / (enc * 1e-3) / 1e9, 2),
             "decode_GBps": round(raw / (dec * 1e-3) / 1e9, 2), "ms_per_step": round(tot, 4), "steps": K, "scaling": "strong",
             "width": w, "height": h, "raw_bytes": raw, "compressed_ratio": round(comp / raw, 4),
-            "split": ("block rows over %d ranks; timed: encode + all-gather of (n_blocks, payload_words) + NCCL send/recv of "
-                      "parts into the spliced stream + splice kernel, then cut + send/recv + finish + decode" % D.world)
-                     if D.world > 1 else "none (one GPU)",
+            "split": ("none (one GPU)" if D.world == 1 else
+                      ("block rows over %d ranks, PEER MEMORY; timed: plan (histograms, tables, slots) + device-side all-gather of "
+                       "the payload sizes + pack kernels writing straight into rank 0's buffer over NVLink + header, then every "
+                       "rank pulls its part out of rank 0's buffer, finishes and decodes it; no host synchronisation" % D.world)
+                      if how == "peer" else
+                      ("block rows over %d ranks; timed: encode + all-gather of (n_blocks, payload_words) + NCCL send/recv of "
+                       "parts into the spliced stream + splice kernel, then cut + send/recv + finish + decode" % D.world)),
+            "transport": how if D.world > 1 else None, "peer_memory_unavailable": why,
             "round_trip_verified_on_every_rank": bool(allok), "gpu_launches_this_rank": launches, "data": "synthetic (GPU generator)"}
 
 
@@ -432,6 +453,7 @@ def main():
     ap.add_argument("--workload", default="C2x64", choices=sorted(WORKLOADS))
     ap.add_argument("--flags", type=lambda s: int(s, 0), default=0x01)
     ap.add_argument("--encoder", default="auto", choices=["auto", "fused", "staged"])
+    ap.add_argument("--c4-mode", default="auto", choices=["auto", "peer", "nccl"], help="transport of the C4 block-row split")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")

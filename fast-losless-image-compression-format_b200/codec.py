@@ -77,6 +77,10 @@ def load_library():
         "flic_wait": (i32, [vp, i32]),
         "flic_splice_block_rows_device": (i32, [vp, C.POINTER(vp), C.POINTER(u64), u32, vp, u64, C.POINTER(u64), vp]),
         "flic_splice_plan": (i32, [C.POINTER(u32), C.POINTER(u32), u32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "flic_encode_plan_device": (i32, [vp, vp, u32, u32, u32, u32, vp, vp]),
+        "flic_encode_emit_device": (i32, [vp, vp, u64, u32, u32, vp, vp]),
+        "flic_splice_header_device": (i32, [vp, vp, u64, u32, u32, u32, u32, vp, vp]),
+        "flic_pull_part_device": (i32, [vp, vp, u32, u32, u32, vp, u64, vp, vp]),
         "flic_splice_finish_device": (i32, [vp, vp, C.POINTER(u32), C.POINTER(u32), u32, u32, u32, u32, u32, vp]),
         "flic_split_finish_device": (i32, [vp, vp, u32, u32, u32, u32, vp]),
     }
@@ -93,7 +97,8 @@ EXPORTED = (
     "flic_decode_batch flic_peek flic_splice_block_rows flic_stage_histograms flic_stage_tables "
     "flic_launch_count flic_set_kernel_timing flic_get_kernel_times flic_set_option flic_get_phase_clocks flic_host_register "
     "flic_host_unregister flic_encode_submit flic_decode_submit flic_wait flic_splice_block_rows_device "
-    "flic_splice_plan flic_splice_finish_device flic_split_finish_device"
+    "flic_splice_plan flic_splice_finish_device flic_split_finish_device flic_encode_plan_device "
+    "flic_encode_emit_device flic_splice_header_device flic_pull_part_device"
 ).split()
 
 KERNELS = ("k_histograms", "k_tables", "k_pack", "k_finalize", "k_decode", "k_slots", "k_encode", "k_decode_one")
@@ -276,6 +281,24 @@ class Codec:
         nb = (C.c_uint32 * k)(*[int(x) for x in part_blocks])
         pw = (C.c_uint32 * k)(*[int(x) for x in part_payload_words])
         self._chk(self.lib.flic_splice_finish_device(self.h, _ptr(out), nb, pw, k, w, h_total, c, flags, C.c_void_p(stream)))
+
+    # ---- block-row split with peer memory (stream buffers are raw device addresses: they may be another GPU's) ----
+    def encode_plan_device(self, rows, flags, d_payload_words, stream=0):
+        """rows: [1, h, w, c] CUDA uint8; d_payload_words: CUDA int64[>=1] that receives the part's payload words."""
+        _, h, w, c = rows.shape
+        self._chk(self.lib.flic_encode_plan_device(self.h, _ptr(rows), w, h, c, flags, _ptr(d_payload_words), C.c_void_p(stream)))
+
+    def encode_emit_device(self, stream_ptr, capacity_bytes, total_blocks, first_block, d_base_words, stream=0):
+        self._chk(self.lib.flic_encode_emit_device(self.h, C.c_void_p(int(stream_ptr)), capacity_bytes, total_blocks, first_block,
+                                                   _ptr(d_base_words), C.c_void_p(stream)))
+
+    def splice_header_device(self, stream_ptr, capacity_bytes, w, h_total, c, flags, d_total_words, stream=0):
+        self._chk(self.lib.flic_splice_header_device(self.h, C.c_void_p(int(stream_ptr)), capacity_bytes, w, h_total, c, flags,
+                                                     _ptr(d_total_words), C.c_void_p(stream)))
+
+    def pull_part_device(self, stream_ptr, total_blocks, first_block, part_blocks, part, d_part_bytes, stream=0):
+        self._chk(self.lib.flic_pull_part_device(self.h, C.c_void_p(int(stream_ptr)), total_blocks, first_block, part_blocks,
+                                                 _ptr(part), part.numel(), _ptr(d_part_bytes), C.c_void_p(stream)))
 
     def split_finish_device(self, part, w, h_part, c, flags=PRED_LEFT, stream=0):
         self._chk(self.lib.flic_split_finish_device(self.h, _ptr(part), w, h_part, c, flags, C.c_void_p(stream)))

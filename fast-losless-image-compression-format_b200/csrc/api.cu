@@ -102,6 +102,8 @@ struct flic_ctx {
     // and a decode in flight together (flic_*_submit) each report their own.  h_err: four pinned words —
     // [0] / [1] are read by the encode / decode pipelines, [2..3] by flic_check
     uint32_t *d_err = nullptr;
+    Geo plan_geo{};               // flic_encode_plan_device -> flic_encode_emit_device
+    bool plan_valid = false;
     uint32_t *h_err = nullptr;
     std::mutex span_mu;
     Pipe enc, dec;
@@ -902,6 +904,89 @@ extern "C" int flic_splice_finish_device(flic_ctx *ctx, uint8_t *d_out, const ui
     sp.k = k;
     CU(cudaSetDevice(ctx->device));
     launch_splice_finish((uint32_t *)d_out, sp, w, h_total, c, flags, (cudaStream_t)stream);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return FLIC_OK;
+}
+
+// ---- block-row split with peer memory: the staged encoder in two halves, with the one collective — the
+// all-gather of the parts' payload sizes — between them, and no host synchronisation anywhere.
+extern "C" int flic_encode_plan_device(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t w, uint32_t h, uint32_t c, uint32_t flags,
+                                       uint64_t *d_payload_words, void *stream) {
+    if (!ctx || !d_pixels || !d_payload_words) return FLIC_E_ARG;
+    if (flags & (FLIC_FLAG_ONE_STREAM | FLIC_FLAG_EXACT)) return FLIC_E_UNSUPPORTED;  // positions must follow from the histograms
+    Geo g;
+    int rc = make_geo(d_pixels, 1, w, h, c, flags, &g);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    rc = ensure_workspace(ctx, g.nb, true);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ctx->ws_used && ctx->ws_stream != s) CU(cudaStreamWaitEvent(s, ctx->ev_ws, 0));
+    { KernelTimer t(ctx, FLIC_K_HISTOGRAMS, s);
+      alignas(64) CUtensorMap tm;
+      const bool tma = make_load_map(g, d_pixels, &tm);
+      launch_histograms(d_pixels, g, ctx->d_hist, ctx->d_resid, ctx->d_flat, tma ? &tm : nullptr, s); }
+    { KernelTimer t(ctx, FLIC_K_TABLES, s); launch_tables(ctx->d_hist, g.nb, ctx->d_table, ctx->d_bits, s); }
+    { KernelTimer t(ctx, FLIC_K_SLOTS, s);
+      launch_slots(g, ctx->d_bits, ctx->d_dirE, ctx->d_slot_status, ++ctx->slot_epoch, ~0ull, ctx->d_err, nullptr, nullptr,
+                   ctx->slots_max_grid, s); }
+    launch_part_directory(ctx->d_dirE, g.nb, nullptr, nullptr, (unsigned long long *)d_payload_words, s);
+    ctx->launches += 4;
+    ctx->plan_geo = g; ctx->plan_valid = true;
+    CU(cudaEventRecord(ctx->ev_ws, s));
+    ctx->ws_stream = s; ctx->ws_used = true;
+    CU(cudaGetLastError());
+    return FLIC_OK;
+}
+
+extern "C" int flic_encode_emit_device(flic_ctx *ctx, uint8_t *d_stream, uint64_t capacity_bytes, uint32_t total_blocks,
+                                       uint32_t first_block, const uint64_t *d_base_words, void *stream) {
+    if (!ctx || !d_stream || !d_base_words || ((uintptr_t)d_stream & 3u)) return FLIC_E_ARG;
+    if (!ctx->plan_valid) return FLIC_E_ARG;
+    const Geo g = ctx->plan_geo;
+    if ((uint64_t)first_block + g.nb > total_blocks) return FLIC_E_ARG;
+    const uint64_t hdr_words = (uint64_t)kHdrWords + total_blocks + 1;
+    if (capacity_bytes / 4 < hdr_words || hdr_words > 0xFFFFFFFFull) return FLIC_E_CAPACITY;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ctx->ws_used && ctx->ws_stream != s) CU(cudaStreamWaitEvent(s, ctx->ev_ws, 0));
+    launch_part_directory(ctx->d_dirE, g.nb, (const unsigned long long *)d_base_words, (uint32_t *)d_stream + kHdrWords + first_block,
+                          nullptr, s);
+    { KernelTimer t(ctx, FLIC_K_PACK, s);
+      launch_pack(ctx->d_resid, g, ctx->d_table, ctx->d_flat, (uint32_t *)d_stream, capacity_bytes / 4, ctx->d_dirE, ctx->d_err,
+                  ctx->d_status, ctx->d_ticket, ctx->ticket_base, ctx->fused_epoch, s, (const unsigned long long *)d_base_words,
+                  (uint32_t)hdr_words); }
+    ctx->launches += 2;
+    ctx->plan_valid = false;
+    CU(cudaEventRecord(ctx->ev_ws, s));
+    ctx->ws_stream = s; ctx->ws_used = true;
+    CU(cudaGetLastError());
+    return FLIC_OK;
+}
+
+extern "C" int flic_splice_header_device(flic_ctx *ctx, uint8_t *d_stream, uint64_t capacity_bytes, uint32_t w, uint32_t h_total,
+                                         uint32_t c, uint32_t flags, const uint64_t *d_total_words, void *stream) {
+    if (!ctx || !d_stream || !d_total_words || ((uintptr_t)d_stream & 3u) || w == 0 || h_total == 0 || c < 1 || c > 4 || !flags_ok(flags))
+        return FLIC_E_ARG;
+    const uint64_t nb = cdiv(w, kBW) * cdiv(h_total, kBH);
+    if (nb >= (1ull << 32)) return FLIC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    launch_splice_header((uint32_t *)d_stream, w, h_total, c, flags, (uint32_t)nb, (const unsigned long long *)d_total_words,
+                         capacity_bytes / 4, ctx->d_err, (cudaStream_t)stream);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return FLIC_OK;
+}
+
+extern "C" int flic_pull_part_device(flic_ctx *ctx, const uint8_t *d_stream, uint32_t total_blocks, uint32_t first_block,
+                                     uint32_t part_blocks, uint8_t *d_part, uint64_t capacity_bytes, uint64_t *d_part_bytes,
+                                     void *stream) {
+    if (!ctx || !d_stream || !d_part || !d_part_bytes || (((uintptr_t)d_stream | (uintptr_t)d_part) & 3u)) return FLIC_E_ARG;
+    if ((uint64_t)first_block + part_blocks > total_blocks) return FLIC_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    launch_pull_part((const uint32_t *)d_stream, total_blocks, first_block, part_blocks, (uint32_t *)d_part, capacity_bytes / 4,
+                     (unsigned long long *)d_part_bytes, ctx->d_err + 1, (cudaStream_t)stream);
     ctx->launches += 1;
     CU(cudaGetLastError());
     return FLIC_OK;

@@ -218,7 +218,8 @@ bool launch_slots(const Geo &g, const uint32_t *d_bits, unsigned long long *d_di
 // d_status / d_ticket / ticket_base / epoch: look-back state, used by FLIC_FLAG_EXACT only (the launch draws n * nb tickets)
 void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, const uint2 *d_flat, uint32_t *d_streams,
                  uint64_t capacity_words, unsigned long long *d_dirE, uint32_t *d_err, unsigned long long *d_status,
-                 unsigned long long *d_ticket, unsigned long long ticket_base, uint32_t epoch, cudaStream_t s);
+                 unsigned long long *d_ticket, unsigned long long ticket_base, uint32_t epoch, cudaStream_t s,
+                 const unsigned long long *d_part_base = nullptr, uint32_t part_hdr_words = 0);
 void launch_finalize(const Geo &g, const unsigned long long *d_dirE, uint32_t *d_streams,
                      uint64_t capacity_words, unsigned long long *d_offsets, uint32_t *d_err,
                      cudaStream_t s);
@@ -242,5 +243,12 @@ struct SpliceParts {
 void launch_splice_finish(uint32_t *d_out, const SpliceParts &sp, uint32_t w, uint32_t h, uint32_t c, uint32_t flags,
                           cudaStream_t s);
 void launch_split_finish(uint32_t *d_part, uint32_t nb, uint32_t w, uint32_t h, uint32_t c, uint32_t flags, cudaStream_t s);
+// peer-memory split (flic_encode_emit_device / flic_splice_header_device / flic_pull_part_device)
+void launch_part_directory(const unsigned long long *d_dirE, uint32_t part_blocks, const unsigned long long *d_base_words,
+                           uint32_t *d_dir_out, unsigned long long *d_part_words_out, cudaStream_t s);
+void launch_splice_header(uint32_t *d_out, uint32_t w, uint32_t h, uint32_t c, uint32_t flags, uint32_t nb,
+                          const unsigned long long *d_total_words, uint64_t capacity_words, uint32_t *d_err, cudaStream_t s);
+void launch_pull_part(const uint32_t *d_stream, uint32_t total_blocks, uint32_t first_block, uint32_t part_blocks, uint32_t *d_part,
+                      uint64_t capacity_words, unsigned long long *d_part_bytes, uint32_t *d_err, cudaStream_t s);
 
 }  // namespace flic

@@ -875,7 +875,7 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
                                                       unsigned long long *dirE,
                                                       uint32_t *err, PackMul pm, unsigned long long *status,
                                                       unsigned long long *ticket, unsigned long long ticket_base, uint32_t epoch,
-                                                      int grid3) {
+                                                      int grid3, const unsigned long long *__restrict__ part_base, uint32_t part_hdr_words) {
     __shared__ __align__(16) uint32_t stage[kBH * kStagePitch + 4];  // + 4: kLayOne reads one word past a row's last
     __shared__ uint32_t tab[256];  // code | len << 24; 0 for a sole symbol (no bits)
     __shared__ uint8_t nib[256];
@@ -1050,7 +1050,11 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
     __syncthreads();
     if (LAY == kLayExact) { excl = s_excl; slot = s_used; }
     if (s_used > slot || (LAY != kLaySlots && s_used != slot)) return;
-    const unsigned long long base = (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + excl;
+    // part_base (block-row split across GPUs, api.cu flic_encode_emit_device): this launch's blocks are a run of block rows of
+    // a larger image whose spliced stream starts at `streams` — possibly in another GPU's memory, written over NVLink —
+    // with part_hdr_words of header + directory in front of the payload and *part_base payload words of earlier parts.
+    const unsigned long long base = part_base ? (unsigned long long)part_hdr_words + *part_base + excl
+                                              : (unsigned long long)(p.img + 1) * (kHdrWords + g.nb + 1) + excl;
     if (base + slot > capacity_words) {
         if (tid == 0) atomicOr(err, kErrCapacity);
         return;
@@ -1100,14 +1104,15 @@ __global__ void __launch_bounds__(kEncThreads, 8) k_pack(const uint32_t *__restr
 // grid is exactly one CTA per block, so the launch consumes n * nb tickets.
 void launch_pack(const uint32_t *d_resid, const Geo &g, const uint16_t *d_table, const uint2 *d_flat, uint32_t *d_streams,
                  uint64_t capacity_words, unsigned long long *d_dirE, uint32_t *d_err, unsigned long long *d_status,
-                 unsigned long long *d_ticket, unsigned long long ticket_base, uint32_t epoch, cudaStream_t s) {
+                 unsigned long long *d_ticket, unsigned long long ticket_base, uint32_t epoch, cudaStream_t s,
+                 const unsigned long long *d_part_base, uint32_t part_hdr_words) {
     uint64_t total = (uint64_t)g.n * g.nb;
     const PackMul pm = {1u << 8, 1u << 10, 1u << 18, 1u << 26};
     const bool g3 = grid3_ok(g) && !(g.flags & FLIC_FLAG_EXACT);
     const dim3 grid = g3 ? dim3(g.nbx, g.nby, g.n) : dim3((unsigned)total);
 #define FLIC_PACK2(C, LAY) \
     k_pack<C, LAY><<<grid, kEncThreads, 0, s>>>(d_resid, g, d_table, d_flat, d_streams, capacity_words, d_dirE, d_err, pm, \
-                                                d_status, d_ticket, ticket_base, epoch, g3)
+                                                d_status, d_ticket, ticket_base, epoch, g3, d_part_base, part_hdr_words)
 #define FLIC_PACK(C)                                                          \
     do {                                                                      \
         if (g.flags & FLIC_FLAG_EXACT) FLIC_PACK2(C, kLayExact);              \

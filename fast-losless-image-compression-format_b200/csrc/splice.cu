@@ -51,6 +51,63 @@ __global__ void k_split_head(uint32_t *part, uint32_t nb, uint32_t w, uint32_t h
     if (t == kHdrWords) part[kHdrWords] = 0;
 }
 
+// ---- block-row split with peer memory: every GPU writes its part straight into the spliced stream (k_pack with a part
+// base) and its directory entries with k_part_directory; one GPU adds the header; for decode a GPU pulls its part out.
+// dirE: the part's own exclusive slot prefix (k_slots); dir_out: the spliced directory at this part's first block.
+__global__ void __launch_bounds__(256) k_part_directory(const unsigned long long *__restrict__ dirE, uint32_t nb,
+                                                        const unsigned long long *__restrict__ base_words, uint32_t *dir_out) {
+    const unsigned long long base = *base_words;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = tid; i < nb; i += stride) dir_out[i] = (uint32_t)(base + dirE[i]);
+}
+__global__ void k_part_words(const unsigned long long *__restrict__ dirE, uint32_t nb, unsigned long long *out) {
+    if (threadIdx.x == 0) *out = dirE[nb];
+}
+__global__ void k_splice_header(uint32_t *out, uint32_t w, uint32_t h, uint32_t c, uint32_t flags, uint32_t nb,
+                                const unsigned long long *__restrict__ total_words, uint64_t capacity_words, uint32_t *err) {
+    const int t = threadIdx.x;
+    const unsigned long long pw = *total_words;
+    if (pw > 0xFFFFFFFFull) { if (t == 0) atomicOr(err, kErrRange); return; }
+    if ((unsigned long long)kHdrWords + nb + 1 + pw > capacity_words) { if (t == 0) atomicOr(err, kErrCapacity); return; }
+    if (t < kHdrWords) write_header(out, w, h, c, flags, nb, (uint32_t)pw, t);
+    if (t == kHdrWords) out[kHdrWords + nb] = (uint32_t)pw;
+}
+// part <- [8 words for the header][directory entries first_block .. first_block + nb][the payload words they span], read
+// from a stream that may live in another GPU's memory (coalesced 4-byte accesses: source and destination are only
+// word-aligned relative to each other).  part_bytes receives the size of the part stream once finished.
+__global__ void __launch_bounds__(256) k_pull_part(const uint32_t *__restrict__ stream, uint32_t total_blocks, uint32_t first_block,
+                                                   uint32_t nb, uint32_t *__restrict__ part, uint64_t capacity_words,
+                                                   unsigned long long *part_bytes, uint32_t *err) {
+    const uint32_t *dir = stream + kHdrWords + first_block;
+    const uint32_t b0 = dir[0], b1 = dir[nb];
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    if (b1 < b0 || (uint64_t)kHdrWords + nb + 1 + (b1 - b0) > capacity_words) {
+        if (tid == 0) { atomicOr(err, b1 < b0 ? kErrFormat : kErrCapacity); *part_bytes = 0; }
+        return;
+    }
+    if (tid == 0) *part_bytes = 4ull * ((uint64_t)kHdrWords + nb + 1 + (b1 - b0));
+    for (uint64_t i = tid; i <= nb; i += stride) part[kHdrWords + i] = dir[i];
+    const uint32_t *src = stream + kHdrWords + total_blocks + 1 + b0;
+    uint32_t *dst = part + kHdrWords + nb + 1;
+    const uint64_t n = b1 - b0;
+    for (uint64_t i = tid; i < n; i += stride) dst[i] = src[i];
+}
+
+void launch_part_directory(const unsigned long long *d_dirE, uint32_t part_blocks, const unsigned long long *d_base_words,
+                           uint32_t *d_dir_out, unsigned long long *d_part_words_out, cudaStream_t s) {
+    if (d_part_words_out) { k_part_words<<<1, 32, 0, s>>>(d_dirE, part_blocks, d_part_words_out); return; }
+    const unsigned grid = (unsigned)((part_blocks + 255) / 256 < 1 ? 1 : ((part_blocks + 255) / 256 > 1184 ? 1184 : (part_blocks + 255) / 256));
+    k_part_directory<<<grid, 256, 0, s>>>(d_dirE, part_blocks, d_base_words, d_dir_out);
+}
+void launch_splice_header(uint32_t *d_out, uint32_t w, uint32_t h, uint32_t c, uint32_t flags, uint32_t nb,
+                          const unsigned long long *d_total_words, uint64_t capacity_words, uint32_t *d_err, cudaStream_t s) {
+    k_splice_header<<<1, 32, 0, s>>>(d_out, w, h, c, flags, nb, d_total_words, capacity_words, d_err);
+}
+void launch_pull_part(const uint32_t *d_stream, uint32_t total_blocks, uint32_t first_block, uint32_t part_blocks, uint32_t *d_part,
+                      uint64_t capacity_words, unsigned long long *d_part_bytes, uint32_t *d_err, cudaStream_t s) {
+    k_pull_part<<<148 * 8, 256, 0, s>>>(d_stream, total_blocks, first_block, part_blocks, d_part, capacity_words, d_part_bytes, d_err);
+}
+
 void launch_splice_finish(uint32_t *d_out, const SpliceParts &sp, uint32_t w, uint32_t h, uint32_t c, uint32_t flags,
                           cudaStream_t s) {
     const uint32_t nb = sp.first_block[sp.k];

@@ -5,13 +5,19 @@
   after which every rank knows where its directory entries and payload land in the spliced stream and
   sends them straight there; rank 0 finishes the splice (header + directory rebase).
 
-Two implementations of the second path:
+Three implementations of the second path:
 
 * `encode_image_sharded` — host logic over any torch.distributed backend (gloo in the CPU tests), with
   the encode and splice functions injected so it is testable without a GPU;
-* `ShardedImageCodec` — the device path used by bench.py's C4 line: parts never leave HBM, the
-  payloads travel by NCCL send/recv (NVLink) directly into their final position, and the directory
-  rebase runs as a kernel (`flic_splice_finish_device` / `flic_split_finish_device`).
+* `ShardedImageCodec` — a device path: parts never leave HBM, the payloads travel by NCCL send/recv
+  (NVLink) directly into their final position, and the directory rebase runs as a kernel
+  (`flic_splice_finish_device` / `flic_split_finish_device`).  The sizes visit the host (NCCL needs them
+  to address its sends): two host synchronisations per direction;
+* `PeerImageCodec` — the path bench.py's C4 line uses when peer memory is available: the spliced stream
+  lives in a torch symmetric-memory buffer on rank 0 that every rank has mapped; every rank's pack
+  kernel writes its block payloads straight into it over NVLink while it packs (compute and transfer in
+  ONE kernel, flic_encode_emit_device), after a device-side all-gather of the part sizes; for decode every
+  rank pulls its part out of rank 0's memory with a copy kernel.  Nothing synchronises with the host.
 """
 import numpy as np
 
@@ -180,4 +186,82 @@ class ShardedImageCodec:
         self.codec.split_finish_device(self.part, self.w, self.y1 - self.y0, self.c, self.flags, stream)
         self.part_off[1] = HEADER_BYTES + 4 * (nbs[r] + 1) + 4 * pws[r]
         self.codec.decode_batch_device(self.part, self.part_off, self.out, self.flags, stream)
+        return self.out
+
+
+class PeerImageCodec:
+    """One w x h x c image split by block rows over the ranks of a NCCL process group, spliced through PEER MEMORY.
+
+    The stream buffer is allocated as torch symmetric memory (one buffer per rank, all mapped into every process; only
+    rank 0's is written).  encode(rows): every rank plans its part (histograms, tables, slot positions), the payload
+    sizes are all-gathered on the device (8 bytes per rank — the only collective that carries data), an exclusive prefix
+    sum gives every rank its base, and flic_encode_emit_device packs the part straight into rank 0's buffer over NVLink;
+    a one-element all-reduce orders rank 0's header write (and any reader) behind everybody's stores.  decode(): every
+    rank copies its directory entries and payload out of rank 0's buffer (flic_pull_part_device), finishes them into a
+    stand-alone stream and decodes its rows.  No call synchronises with the host; sizes never leave device memory.
+    Raises RuntimeError when symmetric memory cannot be set up (the caller then uses ShardedImageCodec)."""
+
+    def __init__(self, codec, w, h, c, flags, dist, rank, world, device="cuda"):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        from .codec import max_stream_bytes
+
+        if flags & 0x60:
+            raise RuntimeError("the peer-memory split needs the default layout (positions from the histograms)")
+        self.torch, self.codec, self.dist = torch, codec, dist
+        self.w, self.h, self.c, self.flags, self.rank, self.world = w, h, c, flags, rank, world
+        self.rows = [block_row_slice(h, r, world) for r in range(world)]
+        self.y0, self.y1 = self.rows[rank]
+        self.nbx = (w + BLOCK_W - 1) // BLOCK_W
+        self.nbs = [self.nbx * ((b - a + BLOCK_H - 1) // BLOCK_H) for a, b in self.rows]
+        self.first = [0]
+        for nb in self.nbs:
+            self.first.append(self.first[-1] + nb)
+        self.total_blocks = self.first[-1]
+        my_rows = max(self.y1 - self.y0, 1)
+        self.cap = max_stream_bytes(w, h, c)
+        # symmetric memory: same size on every rank (only rank 0's buffer holds the stream)
+        self.full = symm_mem.empty(self.cap, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.full, dist.group.WORLD.group_name)
+        self.root_ptr = int(self.hdl.buffer_ptrs[0])
+        self.part = torch.empty(max_stream_bytes(w, my_rows, c), dtype=torch.uint8, device=device)
+        self.part_off = torch.zeros(2, dtype=torch.int64, device=device)
+        self.mine = torch.zeros(1, dtype=torch.int64, device=device)
+        self.totals = torch.zeros(world, dtype=torch.int64, device=device)
+        self.bases = torch.zeros(world + 1, dtype=torch.int64, device=device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.out = torch.empty((1, my_rows, w, c), dtype=torch.uint8, device=device)
+
+    def _fence(self):
+        """Orders everything the ranks have queued so far before everything queued after it, on the device: a one-element
+        all-reduce runs behind each rank's earlier kernels and completes only when every rank has contributed."""
+        self.dist.all_reduce(self.flag)
+
+    def encode(self, rows, stream=0):
+        torch, dist, r = self.torch, self.dist, self.rank
+        if self.y1 > self.y0:
+            self.codec.encode_plan_device(rows, self.flags, self.mine, stream)
+        else:
+            self.mine.zero_()
+        dist.all_gather_into_tensor(self.totals, self.mine)          # the tiny all-gather (sizes stay on the device)
+        self.bases[1:] = torch.cumsum(self.totals, 0)
+        if self.y1 > self.y0:
+            self.codec.encode_emit_device(self.root_ptr, self.cap, self.total_blocks, self.first[r], self.bases[r:], stream)
+        self._fence()
+        if r == 0:
+            self.codec.splice_header_device(self.root_ptr, self.cap, self.w, self.h, self.c, self.flags, self.bases[self.world:], stream)
+        return self.full if r == 0 else None
+
+    def stream_bytes(self):
+        """Size of the spliced stream (a host read: call it outside timed regions)."""
+        return HEADER_BYTES + 4 * (self.total_blocks + 1) + 4 * int(self.bases[self.world].item())
+
+    def decode(self, stream_full=None, stream=0):
+        r = self.rank
+        self._fence()                                                # rank 0's header is in place before anybody reads
+        if self.y1 > self.y0:
+            self.codec.pull_part_device(self.root_ptr, self.total_blocks, self.first[r], self.nbs[r], self.part, self.part_off[1:], stream)
+            self.codec.split_finish_device(self.part, self.w, self.y1 - self.y0, self.c, self.flags, stream)
+            self.codec.decode_batch_device(self.part, self.part_off, self.out, self.flags, stream)
+        self._fence()                                                # every rank has its part: the buffer may be reused
         return self.out

@@ -188,6 +188,32 @@ int flic_splice_finish_device(flic_ctx *ctx, uint8_t *d_out, const uint32_t *par
 int flic_split_finish_device(flic_ctx *ctx, uint8_t *d_part, uint32_t w, uint32_t h_part, uint32_t c,
                              uint32_t flags, void *stream);
 
+/* ---- the same split with PEER MEMORY: pack straight into another GPU's buffer over NVLink ----
+ * One process per GPU; d_stream is the spliced stream's buffer, which may live on another GPU and be mapped into
+ * this process (CUDA IPC / torch symmetric memory).  No host synchronisation anywhere; the only collective is the
+ * all-gather of the parts' payload sizes between the two halves of the encoder:
+ *   flic_encode_plan_device   histograms, code tables and slot positions of this GPU's block rows (default layout
+ *                             only: positions must follow from the histograms); *d_payload_words (device) = the
+ *                             part's payload size in words;
+ *   (caller)                  all-gather the sizes, exclusive prefix sum -> *d_base_words (device) per GPU;
+ *   flic_encode_emit_device   packs the planned part: block payloads at word 8 + total_blocks + 1 + *d_base_words +
+ *                             (offset within the part) of d_stream, directory entries at word 8 + first_block + i;
+ *   flic_splice_header_device (one GPU, after all parts are in: e.g. behind a tiny all-reduce) the 8 header words and
+ *                             the final directory entry, from the device-side total;
+ *   flic_pull_part_device     decode side: copies directory entries first_block .. first_block + part_blocks and the
+ *                             payload they span out of d_stream into d_part (laid out for flic_split_finish_device);
+ *                             *d_part_bytes (device) = size of the part stream. */
+int flic_encode_plan_device(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t w, uint32_t h, uint32_t c,
+                            uint32_t flags, uint64_t *d_payload_words, void *stream);
+int flic_encode_emit_device(flic_ctx *ctx, uint8_t *d_stream, uint64_t capacity_bytes, uint32_t total_blocks,
+                            uint32_t first_block, const uint64_t *d_base_words, void *stream);
+int flic_splice_header_device(flic_ctx *ctx, uint8_t *d_stream, uint64_t capacity_bytes, uint32_t w,
+                              uint32_t h_total, uint32_t c, uint32_t flags, const uint64_t *d_total_words,
+                              void *stream);
+int flic_pull_part_device(flic_ctx *ctx, const uint8_t *d_stream, uint32_t total_blocks, uint32_t first_block,
+                          uint32_t part_blocks, uint8_t *d_part, uint64_t capacity_bytes,
+                          uint64_t *d_part_bytes, void *stream);
+
 /* ---- stage-level entry points (used by the parity tests) ---------------- */
 /* Per-block residual histograms: d_hist[n_blocks_total][256] u16, flat channels left out;
  * d_flat (may be NULL): [n_blocks_total][2] u32 = {flat-channel mask, packed flat values}. */

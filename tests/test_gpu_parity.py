@@ -538,6 +538,54 @@ def test_device_splice_and_split(codec, oracle, flags):
     assert np.array_equal(codec.decode(part.cpu().numpy()), img[96:160])
 
 
+@pytest.mark.parametrize("flags", [0x01, 0x11])
+def test_peer_memory_split_on_one_gpu(codec, oracle, flags):
+    """The peer-memory form of the block-row split (flic_encode_plan_device / _emit_device / flic_splice_header_device /
+    flic_pull_part_device), with one GPU playing every rank in turn and its own memory as the "peer" buffer: the spliced
+    stream equals the model's encode of the whole image, and every part pulled back out decodes to its rows.  No value
+    ever visits the host between the calls (sizes and bases stay in device memory), as across GPUs."""
+    import flic_b200 as flic
+    from flic_b200 import sharding
+    for img in (cases.gradient(700, 200, 4, 43), cases.noise(300, 131, 3, 44), cases.gradient(130, 33, 1, 45)):
+        h, w, c = img.shape
+        k = 3
+        rows = [sharding.block_row_slice(h, r, k) for r in range(k)]
+        nbx = -(-w // 128)
+        nbs = [nbx * (-(-(b - a) // 32)) for a, b in rows]
+        first = [0] + list(np.cumsum(nbs))
+        total_blocks = int(first[-1])
+        cap = flic.max_stream_bytes(w, h, c)
+        full = torch.full((cap,), 0xA5, dtype=torch.uint8, device="cuda")
+        totals = torch.zeros(k, dtype=torch.int64, device="cuda")
+        bases = torch.zeros(k + 1, dtype=torch.int64, device="cuda")
+        px = dev(img)[None]
+        for r, (a, b) in enumerate(rows):
+            if b <= a:
+                continue
+            codec.encode_plan_device(px[:, a:b].contiguous(), flags, totals[r:])
+            bases[1:] = torch.cumsum(totals, 0)                  # what the all-gather + prefix sum gives every rank
+            codec.encode_emit_device(full.data_ptr(), cap, total_blocks, int(first[r]), bases[r:])
+        codec.splice_header_device(full.data_ptr(), cap, w, h, c, flags, bases[k:])
+        codec.check()
+        want = oracle.encode(img, flags)
+        size = 32 + 4 * (total_blocks + 1) + 4 * int(bases[k])
+        assert size == want.size
+        assert np.array_equal(full[:size].cpu().numpy(), want)
+        assert bool((full[size:] == 0xA5).all()), "wrote past the stream"
+        for r, (a, b) in enumerate(rows):
+            if b <= a:
+                continue
+            part = torch.zeros(flic.max_stream_bytes(w, b - a, c), dtype=torch.uint8, device="cuda")
+            off = torch.zeros(2, dtype=torch.int64, device="cuda")
+            codec.pull_part_device(full.data_ptr(), total_blocks, int(first[r]), nbs[r], part, off[1:])
+            codec.split_finish_device(part, w, b - a, c, flags)
+            out = torch.zeros((1, b - a, w, c), dtype=torch.uint8, device="cuda")
+            codec.decode_batch_device(part, off, out, flags)
+            codec.check()
+            assert np.array_equal(out[0].cpu().numpy(), img[a:b])
+            assert np.array_equal(part[: int(off[1])].cpu().numpy(), oracle.encode(img[a:b], flags))
+
+
 def test_offsets_beyond_4gib(codec):
     """BASELINE config 3's shape at its full size on one GPU — 1024 x 1080p RGB, 6.4 GB of pixels — with half of the
     images noise, so that the streams total more than 4 GiB: u64 stream offsets, u32 directories per image."""
