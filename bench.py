@@ -539,14 +539,14 @@ def main():
     dom = max(slow, key=lambda k: kernels[k]["avg_ms"]) if slow else None
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r02_traffic_c2x64.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02b_traffic_c2x64.json")) as f:
             tj = json.load(f)
         if tj.get("workload") == args.workload:
             for k in kernels:
                 if k in tj["kernels"]:
                     kernels[k]["dram_traffic_bytes"] = tj["kernels"][k]["traffic_bytes"]
             if dom in tj["kernels"]:
-                traffic, traffic_src = tj["kernels"][dom]["traffic_bytes"], "profiles/r02_traffic_c2x64.json (ncu dram__bytes_read+write per launch)"
+                traffic, traffic_src = tj["kernels"][dom]["traffic_bytes"], "profiles/r02b_traffic_c2x64.json (ncu dram__bytes_read+write per launch)"
     except Exception:
         pass
     path_frac = min(enc_frac, dec_frac)
