@@ -1,22 +1,25 @@
 // encode.cu — the encode kernels of the FLP0 engine (sm_100a): a staged pipeline of five kernels and a fused
-// single-pass kernel that produce identical bytes (DESIGN.md §4.1, §4.2, §5.2 for when each is used and why).
+// single-pass kernel that produce identical bytes in every layout (DESIGN.md §4.1, §4.2, §5.2 for when each is used and why).
 //
 //  staged (large batches: every stage at full occupancy, the serial Huffman merges of eight blocks share a warp)
-//   k_histograms : one CTA per block; the block's pixels arrive as ONE TMA tile load (cp.async.bulk.tensor +
-//                  mbarrier; direct 128-bit loads when the batch is not 16-byte aligned), residuals in
-//                  registers, written to the residual plane with ONE bulk store, warp-privatised shared-memory
-//                  histograms, flat-channel detection (FLP0 §2b), 512 B of u16 counts per block.
-//   k_tables     : one WARP per 8 blocks; bitonic sort of (count,symbol) keys, two-queue Huffman merge (one
-//                  block per lane), depth census, Kraft repair, lengths by rank, canonical code assignment by
+//   k_histograms : one CTA per block, grid (nbx, nby, n); the block's pixels arrive as ONE TMA tile load
+//                  (cp.async.bulk.tensor + mbarrier; direct 128-bit loads when the batch is not 16-byte aligned),
+//                  residuals in registers, written to the residual plane with ONE bulk store, 2-4 shared sub-histograms
+//                  whose increments address with one LOP3, flat-channel detection (FLP0 §2b), 512 B of u16 counts per block.
+//   k_tables     : one WARP per 8 blocks, four warps per CTA; bitonic sort of (count,symbol) keys, two-queue Huffman
+//                  merge (one block per lane), depth census, Kraft repair, lengths by rank, canonical code assignment by
 //                  packed-counter warp scan, and the block's total of count x code length.
-//   k_slots      : exclusive prefix sum of block slot sizes (FLP0 §7): every block's output position is known
-//                  before anything is packed.
-//   k_pack       : one CTA per block; reads the residual plane, merges four symbols into a code group, warp scan
-//                  of bit lengths, RED.OR of every group into a zeroed shared staging tile at its end bit position,
-//                  interleaving copy-out straight into the block's slot.
+//   k_slots      : exclusive prefix sum of block sizes where they follow from the histograms (slots: FLP0 §7; ONE_STREAM:
+//                  exact): every block's output position is known before anything is packed.
+//   k_pack       : one CTA per block; reads the residual plane, merges symbols into code groups (three per group and two
+//                  groups per placement for opaque-alpha RGBA), warp scan of bit lengths, RED.OR of every group into a
+//                  zeroed shared staging tile at its end bit position; copy-out by layout: interleaved rows into the
+//                  block's slot / the rows concatenated bit-exactly (ONE_STREAM) / ticket order + decoupled look-back
+//                  over the packed sizes (EXACT); optionally into a larger image's spliced stream on another GPU
+//                  (block-row split through peer memory).
 //   k_finalize   : headers, rebased u32 directories and the n+1 stream offsets.
 //
-//  fused (small jobs, FLIC_FLAG_EXACT, FLIC_FLAG_ONE_STREAM)
+//  fused (small jobs)
 //   k_encode     : persistent CTAs; per block: rows -> residuals parked in shared memory -> histogram -> code table
 //                  built by the whole CTA (cta_table) -> rows packed over the same tile -> position by a decoupled
 //                  look-back over the predecessors' sizes -> copy-out.  Pixels are read once; nothing but the
