@@ -52,7 +52,7 @@ extern "C" {
  *              decoder where a row starts, so parallel decode has to self-synchronise (k_decode_one).
  *  EXACT       per-row sub-streams as usual, but a block occupies exactly the words it uses (slack 0):
  *              its size is NOT known before it is packed, so the encoder places blocks with a
- *              single-pass decoupled look-back over the packed sizes instead of precomputed slots. */
+ *              decoupled look-back over the packed sizes instead of precomputed slots. */
 #define FLIC_FLAG_ONE_STREAM 0x20u
 #define FLIC_FLAG_EXACT 0x40u
 #define FLIC_FLAGS_ALL 0x7Fu
@@ -71,14 +71,16 @@ const char *flic_strerror(int code);
 const char *flic_last_error(const flic_ctx *ctx); /* detail of the last FLIC_E_CUDA / _INTERNAL */
 int flic_version(void);
 
-/* Options.  FLIC_OPT_ENCODER selects the encode path for plain FLP0 v3 streams; both produce identical bytes.
+/* Options.  FLIC_OPT_ENCODER selects the encode path; both produce identical bytes, in every layout.
  *   FUSED   one persistent kernel: pixels are read once, residuals never leave the SM, blocks are placed by a
  *           decoupled look-back (2 launches per call, DRAM traffic = the algorithmic bytes);
  *   STAGED  the five-kernel pipeline with a residual plane in HBM (2.4x the algorithmic DRAM bytes, but every
  *           stage runs at full occupancy and the serial Huffman merges of eight blocks share a warp — on B200
  *           this path is bound by issue slots, not by HBM, and is the faster one for large batches);
  *   AUTO    (default) FUSED for small jobs, where launch count and latency matter, STAGED for large ones.
- * FLIC_FLAG_ONE_STREAM / FLIC_FLAG_EXACT streams always take the fused kernel.  The environment variable
+ * With FLIC_FLAG_ONE_STREAM the staged pipeline's pack kernel concatenates the rows bit-exactly (the block sizes are
+ * exact and still follow from the histograms); with FLIC_FLAG_EXACT it takes blocks in ticket order and places them with
+ * the same decoupled look-back over the packed sizes as the fused kernel.  The environment variable
  * FLIC_ENCODER=fused|staged|auto sets the default at flic_create(). */
 #define FLIC_OPT_ENCODER 1
 #define FLIC_ENCODER_FUSED 0
