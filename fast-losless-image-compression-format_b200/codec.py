@@ -80,7 +80,7 @@ def load_library():
         "flic_encode_plan_device": (i32, [vp, vp, u32, u32, u32, u32, vp, vp]),
         "flic_encode_emit_device": (i32, [vp, vp, u64, u32, u32, vp, vp]),
         "flic_splice_header_device": (i32, [vp, vp, u64, u32, u32, u32, u32, vp, vp]),
-        "flic_pull_part_device": (i32, [vp, vp, u32, u32, u32, vp, u64, vp, vp]),
+        "flic_pull_part_device": (i32, [vp, vp, u64, u32, u32, u32, vp, u64, vp, vp]),
         "flic_splice_finish_device": (i32, [vp, vp, C.POINTER(u32), C.POINTER(u32), u32, u32, u32, u32, u32, vp]),
         "flic_split_finish_device": (i32, [vp, vp, u32, u32, u32, u32, vp]),
     }
@@ -296,8 +296,8 @@ class Codec:
         self._chk(self.lib.flic_splice_header_device(self.h, C.c_void_p(int(stream_ptr)), capacity_bytes, w, h_total, c, flags,
                                                      _ptr(d_total_words), C.c_void_p(stream)))
 
-    def pull_part_device(self, stream_ptr, total_blocks, first_block, part_blocks, part, d_part_bytes, stream=0):
-        self._chk(self.lib.flic_pull_part_device(self.h, C.c_void_p(int(stream_ptr)), total_blocks, first_block, part_blocks,
+    def pull_part_device(self, stream_ptr, stream_bytes, total_blocks, first_block, part_blocks, part, d_part_bytes, stream=0):
+        self._chk(self.lib.flic_pull_part_device(self.h, C.c_void_p(int(stream_ptr)), stream_bytes, total_blocks, first_block, part_blocks,
                                                  _ptr(part), part.numel(), _ptr(d_part_bytes), C.c_void_p(stream)))
 
     def split_finish_device(self, part, w, h_part, c, flags=PRED_LEFT, stream=0):

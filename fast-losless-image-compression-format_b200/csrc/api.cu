@@ -979,13 +979,13 @@ extern "C" int flic_splice_header_device(flic_ctx *ctx, uint8_t *d_stream, uint6
     return FLIC_OK;
 }
 
-extern "C" int flic_pull_part_device(flic_ctx *ctx, const uint8_t *d_stream, uint32_t total_blocks, uint32_t first_block,
-                                     uint32_t part_blocks, uint8_t *d_part, uint64_t capacity_bytes, uint64_t *d_part_bytes,
-                                     void *stream) {
+extern "C" int flic_pull_part_device(flic_ctx *ctx, const uint8_t *d_stream, uint64_t stream_bytes, uint32_t total_blocks,
+                                     uint32_t first_block, uint32_t part_blocks, uint8_t *d_part, uint64_t capacity_bytes,
+                                     uint64_t *d_part_bytes, void *stream) {
     if (!ctx || !d_stream || !d_part || !d_part_bytes || (((uintptr_t)d_stream | (uintptr_t)d_part) & 3u)) return FLIC_E_ARG;
     if ((uint64_t)first_block + part_blocks > total_blocks) return FLIC_E_ARG;
     CU(cudaSetDevice(ctx->device));
-    launch_pull_part((const uint32_t *)d_stream, total_blocks, first_block, part_blocks, (uint32_t *)d_part, capacity_bytes / 4,
+    launch_pull_part((const uint32_t *)d_stream, stream_bytes / 4, total_blocks, first_block, part_blocks, (uint32_t *)d_part, capacity_bytes / 4,
                      (unsigned long long *)d_part_bytes, ctx->d_err + 1, (cudaStream_t)stream);
     ctx->launches += 1;
     CU(cudaGetLastError());

@@ -248,7 +248,7 @@ void launch_part_directory(const unsigned long long *d_dirE, uint32_t part_block
                            uint32_t *d_dir_out, unsigned long long *d_part_words_out, cudaStream_t s);
 void launch_splice_header(uint32_t *d_out, uint32_t w, uint32_t h, uint32_t c, uint32_t flags, uint32_t nb,
                           const unsigned long long *d_total_words, uint64_t capacity_words, uint32_t *d_err, cudaStream_t s);
-void launch_pull_part(const uint32_t *d_stream, uint32_t total_blocks, uint32_t first_block, uint32_t part_blocks, uint32_t *d_part,
-                      uint64_t capacity_words, unsigned long long *d_part_bytes, uint32_t *d_err, cudaStream_t s);
+void launch_pull_part(const uint32_t *d_stream, uint64_t stream_words, uint32_t total_blocks, uint32_t first_block, uint32_t part_blocks,
+                      uint32_t *d_part, uint64_t capacity_words, unsigned long long *d_part_bytes, uint32_t *d_err, cudaStream_t s);
 
 }  // namespace flic

@@ -75,19 +75,28 @@ __global__ void k_splice_header(uint32_t *out, uint32_t w, uint32_t h, uint32_t 
 // part <- [8 words for the header][directory entries first_block .. first_block + nb][the payload words they span], read
 // from a stream that may live in another GPU's memory (coalesced 4-byte accesses: source and destination are only
 // word-aligned relative to each other).  part_bytes receives the size of the part stream once finished.
-__global__ void __launch_bounds__(256) k_pull_part(const uint32_t *__restrict__ stream, uint32_t total_blocks, uint32_t first_block,
-                                                   uint32_t nb, uint32_t *__restrict__ part, uint64_t capacity_words,
-                                                   unsigned long long *part_bytes, uint32_t *err) {
-    const uint32_t *dir = stream + kHdrWords + first_block;
-    const uint32_t b0 = dir[0], b1 = dir[nb];
+__global__ void __launch_bounds__(256) k_pull_part(const uint32_t *__restrict__ stream, uint64_t stream_words, uint32_t total_blocks,
+                                                   uint32_t first_block, uint32_t nb, uint32_t *__restrict__ part,
+                                                   uint64_t capacity_words, unsigned long long *part_bytes, uint32_t *err) {
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
-    if (b1 < b0 || (uint64_t)kHdrWords + nb + 1 + (b1 - b0) > capacity_words) {
-        if (tid == 0) { atomicOr(err, b1 < b0 ? kErrFormat : kErrCapacity); *part_bytes = 0; }
+    // the stream is input: nothing is read past what its (validated) header says it holds, nothing past its buffer
+    const uint64_t fixed = (uint64_t)kHdrWords + total_blocks + 1;
+    bool ok = stream_words >= fixed && stream[0] == kMagic && stream[5] == total_blocks && fixed + stream[6] <= stream_words;
+    uint32_t b0 = 0, b1 = 0;
+    if (ok) {
+        b0 = stream[kHdrWords + first_block];
+        b1 = stream[kHdrWords + first_block + nb];
+        ok = b0 <= b1 && b1 <= stream[6];
+    }
+    const bool fits = ok && (uint64_t)kHdrWords + nb + 1 + (b1 - b0) <= capacity_words;
+    if (!fits) {
+        if (tid == 0) { atomicOr(err, ok ? kErrCapacity : kErrFormat); *part_bytes = 0; }
         return;
     }
     if (tid == 0) *part_bytes = 4ull * ((uint64_t)kHdrWords + nb + 1 + (b1 - b0));
+    const uint32_t *dir = stream + kHdrWords + first_block;
     for (uint64_t i = tid; i <= nb; i += stride) part[kHdrWords + i] = dir[i];
-    const uint32_t *src = stream + kHdrWords + total_blocks + 1 + b0;
+    const uint32_t *src = stream + fixed + b0;
     uint32_t *dst = part + kHdrWords + nb + 1;
     const uint64_t n = b1 - b0;
     for (uint64_t i = tid; i < n; i += stride) dst[i] = src[i];
@@ -103,9 +112,10 @@ void launch_splice_header(uint32_t *d_out, uint32_t w, uint32_t h, uint32_t c, u
                           const unsigned long long *d_total_words, uint64_t capacity_words, uint32_t *d_err, cudaStream_t s) {
     k_splice_header<<<1, 32, 0, s>>>(d_out, w, h, c, flags, nb, d_total_words, capacity_words, d_err);
 }
-void launch_pull_part(const uint32_t *d_stream, uint32_t total_blocks, uint32_t first_block, uint32_t part_blocks, uint32_t *d_part,
-                      uint64_t capacity_words, unsigned long long *d_part_bytes, uint32_t *d_err, cudaStream_t s) {
-    k_pull_part<<<148 * 8, 256, 0, s>>>(d_stream, total_blocks, first_block, part_blocks, d_part, capacity_words, d_part_bytes, d_err);
+void launch_pull_part(const uint32_t *d_stream, uint64_t stream_words, uint32_t total_blocks, uint32_t first_block, uint32_t part_blocks,
+                      uint32_t *d_part, uint64_t capacity_words, unsigned long long *d_part_bytes, uint32_t *d_err, cudaStream_t s) {
+    k_pull_part<<<148 * 8, 256, 0, s>>>(d_stream, stream_words, total_blocks, first_block, part_blocks, d_part, capacity_words, d_part_bytes,
+                                        d_err);
 }
 
 void launch_splice_finish(uint32_t *d_out, const SpliceParts &sp, uint32_t w, uint32_t h, uint32_t c, uint32_t flags,

@@ -260,7 +260,7 @@ class PeerImageCodec:
         r = self.rank
         self._fence()                                                # rank 0's header is in place before anybody reads
         if self.y1 > self.y0:
-            self.codec.pull_part_device(self.root_ptr, self.total_blocks, self.first[r], self.nbs[r], self.part, self.part_off[1:], stream)
+            self.codec.pull_part_device(self.root_ptr, self.cap, self.total_blocks, self.first[r], self.nbs[r], self.part, self.part_off[1:], stream)
             self.codec.split_finish_device(self.part, self.w, self.y1 - self.y0, self.c, self.flags, stream)
             self.codec.decode_batch_device(self.part, self.part_off, self.out, self.flags, stream)
         self._fence()                                                # every rank has its part: the buffer may be reused

@@ -204,7 +204,9 @@ int flic_split_finish_device(flic_ctx *ctx, uint8_t *d_part, uint32_t w, uint32_
  *                             the final directory entry, from the device-side total;
  *   flic_pull_part_device     decode side: copies directory entries first_block .. first_block + part_blocks and the
  *                             payload they span out of d_stream into d_part (laid out for flic_split_finish_device);
- *                             *d_part_bytes (device) = size of the part stream. */
+ *                             *d_part_bytes (device) = size of the part stream.  The stream is treated as input: its
+ *                             header and the two directory entries are validated against stream_bytes (the bytes
+ *                             readable at d_stream) before anything is copied (FLIC_E_FORMAT through flic_check). */
 int flic_encode_plan_device(flic_ctx *ctx, const uint8_t *d_pixels, uint32_t w, uint32_t h, uint32_t c,
                             uint32_t flags, uint64_t *d_payload_words, void *stream);
 int flic_encode_emit_device(flic_ctx *ctx, uint8_t *d_stream, uint64_t capacity_bytes, uint32_t total_blocks,
@@ -212,8 +214,8 @@ int flic_encode_emit_device(flic_ctx *ctx, uint8_t *d_stream, uint64_t capacity_
 int flic_splice_header_device(flic_ctx *ctx, uint8_t *d_stream, uint64_t capacity_bytes, uint32_t w,
                               uint32_t h_total, uint32_t c, uint32_t flags, const uint64_t *d_total_words,
                               void *stream);
-int flic_pull_part_device(flic_ctx *ctx, const uint8_t *d_stream, uint32_t total_blocks, uint32_t first_block,
-                          uint32_t part_blocks, uint8_t *d_part, uint64_t capacity_bytes,
+int flic_pull_part_device(flic_ctx *ctx, const uint8_t *d_stream, uint64_t stream_bytes, uint32_t total_blocks,
+                          uint32_t first_block, uint32_t part_blocks, uint8_t *d_part, uint64_t capacity_bytes,
                           uint64_t *d_part_bytes, void *stream);
 
 /* ---- stage-level entry points (used by the parity tests) ---------------- */

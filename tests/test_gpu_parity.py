@@ -577,13 +577,41 @@ def test_peer_memory_split_on_one_gpu(codec, oracle, flags):
                 continue
             part = torch.zeros(flic.max_stream_bytes(w, b - a, c), dtype=torch.uint8, device="cuda")
             off = torch.zeros(2, dtype=torch.int64, device="cuda")
-            codec.pull_part_device(full.data_ptr(), total_blocks, int(first[r]), nbs[r], part, off[1:])
+            codec.pull_part_device(full.data_ptr(), cap, total_blocks, int(first[r]), nbs[r], part, off[1:])
             codec.split_finish_device(part, w, b - a, c, flags)
             out = torch.zeros((1, b - a, w, c), dtype=torch.uint8, device="cuda")
             codec.decode_batch_device(part, off, out, flags)
             codec.check()
             assert np.array_equal(out[0].cpu().numpy(), img[a:b])
             assert np.array_equal(part[: int(off[1])].cpu().numpy(), oracle.encode(img[a:b], flags))
+
+
+def test_pull_part_refuses_damaged_streams(codec, oracle):
+    """flic_pull_part_device treats the stream as input: a wrong magic, a block count that is not the caller's, a payload
+    size beyond the buffer, a directory entry beyond the payload or a descending pair are FLIC_E_FORMAT, and nothing is copied."""
+    import flic_b200 as flic
+    img = cases.gradient(300, 100, 3, 46)
+    good = oracle.encode(img)
+    nb = int(flic.peek(good)["n_blocks"])
+    nbx = -(-300 // 128)
+    for word, value in ((0, 0x12345678), (5, nb + 1), (6, 1 << 30), (8 + nbx, 0xFFFFFFF0), (8 + 2 * nbx, 0)):
+        bad = good.copy()
+        bad.view(np.uint32)[word] = value
+        d = dev(bad)
+        part = torch.full((good.size,), 0xA5, dtype=torch.uint8, device="cuda")
+        off = torch.ones(2, dtype=torch.int64, device="cuda")
+        codec.pull_part_device(d.data_ptr(), d.numel(), nb, nbx, nbx, part, off[1:])
+        with pytest.raises(flic.FlicError) as ei:
+            codec.check()
+        assert ei.value.code == -3, (word, ei.value.code)
+        assert int(off[1]) == 0 and bool((part == 0xA5).all())
+    d = dev(good)
+    part = torch.zeros(good.size, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(2, dtype=torch.int64, device="cuda")
+    codec.pull_part_device(d.data_ptr(), d.numel(), nb, nbx, nbx, part, off[1:])
+    codec.split_finish_device(part, 300, 32, 3)
+    codec.check()
+    assert np.array_equal(part[: int(off[1])].cpu().numpy(), oracle.encode(img[32:64]))
 
 
 def test_offsets_beyond_4gib(codec):
