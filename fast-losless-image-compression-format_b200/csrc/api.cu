@@ -931,7 +931,7 @@ extern "C" int flic_encode_plan_device(flic_ctx *ctx, const uint8_t *d_pixels, u
     { KernelTimer t(ctx, FLIC_K_SLOTS, s);
       launch_slots(g, ctx->d_bits, ctx->d_dirE, ctx->d_slot_status, ++ctx->slot_epoch, ~0ull, ctx->d_err, nullptr, nullptr,
                    ctx->slots_max_grid, s); }
-    launch_part_directory(ctx->d_dirE, g.nb, nullptr, nullptr, (unsigned long long *)d_payload_words, s);
+    launch_part_words(ctx->d_dirE, g.nb, (unsigned long long *)d_payload_words, s);
     ctx->launches += 4;
     ctx->plan_geo = g; ctx->plan_valid = true;
     CU(cudaEventRecord(ctx->ev_ws, s));
@@ -951,8 +951,7 @@ extern "C" int flic_encode_emit_device(flic_ctx *ctx, uint8_t *d_stream, uint64_
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
     if (ctx->ws_used && ctx->ws_stream != s) CU(cudaStreamWaitEvent(s, ctx->ev_ws, 0));
-    launch_part_directory(ctx->d_dirE, g.nb, (const unsigned long long *)d_base_words, (uint32_t *)d_stream + kHdrWords + first_block,
-                          nullptr, s);
+    launch_part_directory(ctx->d_dirE, g.nb, (const unsigned long long *)d_base_words, (uint32_t *)d_stream + kHdrWords + first_block, s);
     { KernelTimer t(ctx, FLIC_K_PACK, s);
       launch_pack(ctx->d_resid, g, ctx->d_table, ctx->d_flat, (uint32_t *)d_stream, capacity_bytes / 4, ctx->d_dirE, ctx->d_err,
                   ctx->d_status, ctx->d_ticket, ctx->ticket_base, ctx->fused_epoch, s, (const unsigned long long *)d_base_words,

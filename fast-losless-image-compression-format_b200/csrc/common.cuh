@@ -244,8 +244,9 @@ void launch_splice_finish(uint32_t *d_out, const SpliceParts &sp, uint32_t w, ui
                           cudaStream_t s);
 void launch_split_finish(uint32_t *d_part, uint32_t nb, uint32_t w, uint32_t h, uint32_t c, uint32_t flags, cudaStream_t s);
 // peer-memory split (flic_encode_emit_device / flic_splice_header_device / flic_pull_part_device)
+void launch_part_words(const unsigned long long *d_dirE, uint32_t part_blocks, unsigned long long *d_part_words_out, cudaStream_t s);
 void launch_part_directory(const unsigned long long *d_dirE, uint32_t part_blocks, const unsigned long long *d_base_words,
-                           uint32_t *d_dir_out, unsigned long long *d_part_words_out, cudaStream_t s);
+                           uint32_t *d_dir_out, cudaStream_t s);
 void launch_splice_header(uint32_t *d_out, uint32_t w, uint32_t h, uint32_t c, uint32_t flags, uint32_t nb,
                           const unsigned long long *d_total_words, uint64_t capacity_words, uint32_t *d_err, cudaStream_t s);
 void launch_pull_part(const uint32_t *d_stream, uint64_t stream_words, uint32_t total_blocks, uint32_t first_block, uint32_t part_blocks,

@@ -102,9 +102,11 @@ __global__ void __launch_bounds__(256) k_pull_part(const uint32_t *__restrict__ 
     for (uint64_t i = tid; i < n; i += stride) dst[i] = src[i];
 }
 
+void launch_part_words(const unsigned long long *d_dirE, uint32_t part_blocks, unsigned long long *d_part_words_out, cudaStream_t s) {
+    k_part_words<<<1, 32, 0, s>>>(d_dirE, part_blocks, d_part_words_out);
+}
 void launch_part_directory(const unsigned long long *d_dirE, uint32_t part_blocks, const unsigned long long *d_base_words,
-                           uint32_t *d_dir_out, unsigned long long *d_part_words_out, cudaStream_t s) {
-    if (d_part_words_out) { k_part_words<<<1, 32, 0, s>>>(d_dirE, part_blocks, d_part_words_out); return; }
+                           uint32_t *d_dir_out, cudaStream_t s) {
     const unsigned grid = (unsigned)((part_blocks + 255) / 256 < 1 ? 1 : ((part_blocks + 255) / 256 > 1184 ? 1184 : (part_blocks + 255) / 256));
     k_part_directory<<<grid, 256, 0, s>>>(d_dirE, part_blocks, d_base_words, d_dir_out);
 }

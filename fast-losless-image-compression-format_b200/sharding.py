@@ -201,9 +201,10 @@ class PeerImageCodec:
     stand-alone stream and decodes its rows.  No call synchronises with the host; sizes never leave device memory.
     Raises RuntimeError when symmetric memory cannot be set up (the caller then uses ShardedImageCodec)."""
 
-    def __init__(self, codec, w, h, c, flags, dist, rank, world, device="cuda"):
+    def __init__(self, codec, w, h, c, flags, dist, rank, world, device="cuda", alloc=None):
+        """alloc (tests): nbytes -> (this rank's buffer, what to hand the codec as rank 0's buffer); the default allocates
+        torch symmetric memory and hands the codec rank 0's device address."""
         import torch
-        import torch.distributed._symmetric_memory as symm_mem
         from .codec import max_stream_bytes
 
         if flags & 0x60:
@@ -220,10 +221,14 @@ class PeerImageCodec:
         self.total_blocks = self.first[-1]
         my_rows = max(self.y1 - self.y0, 1)
         self.cap = max_stream_bytes(w, h, c)
-        # symmetric memory: same size on every rank (only rank 0's buffer holds the stream)
-        self.full = symm_mem.empty(self.cap, dtype=torch.uint8, device=device)
-        self.hdl = symm_mem.rendezvous(self.full, dist.group.WORLD.group_name)
-        self.root_ptr = int(self.hdl.buffer_ptrs[0])
+        if alloc is None:
+            # symmetric memory: same size on every rank (only rank 0's buffer holds the stream)
+            import torch.distributed._symmetric_memory as symm_mem
+            self.full = symm_mem.empty(self.cap, dtype=torch.uint8, device=device)
+            self.hdl = symm_mem.rendezvous(self.full, dist.group.WORLD.group_name)
+            self.root_ptr = int(self.hdl.buffer_ptrs[0])
+        else:
+            self.full, self.root_ptr = alloc(self.cap)
         self.part = torch.empty(max_stream_bytes(w, my_rows, c), dtype=torch.uint8, device=device)
         self.part_off = torch.zeros(2, dtype=torch.int64, device=device)
         self.mine = torch.zeros(1, dtype=torch.int64, device=device)

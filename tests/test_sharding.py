@@ -152,3 +152,86 @@ def test_sharded_codec_exchange_world2(flic, oracle, shape, flags):
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert all(res), res
+
+
+# ---- the peer-memory path's host logic (PeerImageCodec) over gloo: the "peer buffer" is a file both processes map, the
+# engine is replaced by the model and numpy restatements of the small kernels
+class _ModelPeerCodec(_ModelCodec):
+    def encode_plan_device(self, rows, flags, d_payload_words, stream=0):
+        self.planned = self.orc.encode(rows[0].numpy(), flags).view(np.uint32)
+        d_payload_words[0] = int(self.planned[6])
+
+    def encode_emit_device(self, root, capacity_bytes, total_blocks, first_block, d_base_words, stream=0):
+        o, p = root.numpy().view(np.uint32), self.planned
+        nb, pw, base = int(p[5]), int(p[6]), int(d_base_words[0])
+        o[8 + first_block: 8 + first_block + nb] = p[8: 8 + nb] + np.uint32(base)
+        pay = 8 + total_blocks + 1 + base
+        assert 4 * (pay + pw) <= capacity_bytes
+        o[pay: pay + pw] = p[8 + nb + 1: 8 + nb + 1 + pw]
+
+    def splice_header_device(self, root, capacity_bytes, w, h, c, flags, d_total_words, stream=0):
+        o = root.numpy().view(np.uint32)
+        nb, pw = -(-w // 128) * -(-h // 32), int(d_total_words[0])
+        o[:8] = self._header(w, h, c, flags, nb, pw)
+        o[8 + nb] = pw
+
+    def pull_part_device(self, root, stream_bytes, total_blocks, first_block, nb, part, d_part_bytes, stream=0):
+        o, q = root.numpy().view(np.uint32), part.numpy().view(np.uint32)
+        assert o[0] == 0x30504C46 and o[5] == total_blocks
+        b0, b1 = int(o[8 + first_block]), int(o[8 + first_block + nb])
+        q[8: 8 + nb + 1] = o[8 + first_block: 8 + first_block + nb + 1]
+        q[8 + nb + 1: 8 + nb + 1 + (b1 - b0)] = o[8 + total_blocks + 1 + b0: 8 + total_blocks + 1 + b1]
+        d_part_bytes[0] = 4 * (8 + nb + 1 + (b1 - b0))
+
+
+def _worker_peer(rank, world, port, shape, flags, path, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import flic_b200 as flic
+        import oracle_binding
+        orc = oracle_binding.Oracle(os.path.join(ROOT, "oracle", "libflp0_oracle.so"))
+        h, w, c = shape
+        img = cases.gradient(w, h, c, 79)
+
+        def alloc(nbytes):  # one file, mapped shared by every rank: rank 0's "buffer" is everybody's
+            t = torch.from_file(path, shared=True, size=nbytes, dtype=torch.uint8)
+            return t, t
+
+        sc = flic.sharding.PeerImageCodec(_ModelPeerCodec(orc), w, h, c, flags, dist, rank, world, device="cpu", alloc=alloc)
+        rows = torch.from_numpy(img[sc.y0: sc.y1][None].copy())
+        ok = True
+        for _ in range(2):  # twice: the buffer is reused
+            full = sc.encode(rows)
+            if rank == 0:
+                want = orc.encode(img, flags)
+                ok = ok and sc.stream_bytes() == want.size and bool(np.array_equal(full.numpy()[: want.size], want))
+            out = sc.decode()
+            if sc.y1 > sc.y0:  # (a rank that owns no block row has nothing to compare)
+                ok = ok and bool(np.array_equal(out[0].numpy(), img[sc.y0: sc.y1]))
+        q.put(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("shape,flags", [((200, 300, 3), 0x01), ((96, 130, 4), 0x11), ((40, 64, 1), 0x01)])
+def test_peer_codec_protocol(flic, oracle, tmp_path, shape, flags, world):
+    """plan -> all-gather of payload sizes (stays in a tensor) -> prefix sum -> every rank writes its payload and directory
+    entries at its base in rank 0's buffer -> fence -> header; decode: fence -> every rank pulls its part -> finish -> rows.
+    Spliced bytes == the model's encode of the whole image, also when a rank owns no block row (40 rows over 3 ranks)."""
+    import flic_b200 as flic_mod
+    h, w, c = shape
+    path = str(tmp_path / "peer.bin")
+    with open(path, "wb") as f:
+        f.truncate(flic_mod.max_stream_bytes(w, h, c))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_peer, args=(r, world, port, shape, flags, path, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert all(res), res
