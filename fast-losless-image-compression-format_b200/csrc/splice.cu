@@ -79,27 +79,46 @@ __global__ void __launch_bounds__(256) k_pull_part(const uint32_t *__restrict__ 
                                                    uint32_t first_block, uint32_t nb, uint32_t *__restrict__ part,
                                                    uint64_t capacity_words, unsigned long long *part_bytes, uint32_t *err) {
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
-    // the stream is input: nothing is read past what its (validated) header says it holds, nothing past its buffer
+    // the stream is input: nothing is read past what its (validated) header says it holds, nothing past its buffer.
+    // One thread per CTA reads the five words (they may be a NVLink round trip away) and shares the verdict.
     const uint64_t fixed = (uint64_t)kHdrWords + total_blocks + 1;
-    bool ok = stream_words >= fixed && stream[0] == kMagic && stream[5] == total_blocks && fixed + stream[6] <= stream_words;
-    uint32_t b0 = 0, b1 = 0;
-    if (ok) {
-        b0 = stream[kHdrWords + first_block];
-        b1 = stream[kHdrWords + first_block + nb];
-        ok = b0 <= b1 && b1 <= stream[6];
+    __shared__ uint32_t s_b0, s_b1, s_state;  // state: 0 ok, else the error bit
+    if (threadIdx.x == 0) {
+        bool ok = stream_words >= fixed && stream[0] == kMagic && stream[5] == total_blocks && fixed + stream[6] <= stream_words;
+        uint32_t b0 = 0, b1 = 0;
+        if (ok) {
+            b0 = stream[kHdrWords + first_block];
+            b1 = stream[kHdrWords + first_block + nb];
+            ok = b0 <= b1 && b1 <= stream[6];
+        }
+        const bool fits = ok && (uint64_t)kHdrWords + nb + 1 + (b1 - b0) <= capacity_words;
+        s_b0 = b0; s_b1 = b1; s_state = fits ? 0u : (ok ? kErrCapacity : kErrFormat);
     }
-    const bool fits = ok && (uint64_t)kHdrWords + nb + 1 + (b1 - b0) <= capacity_words;
-    if (!fits) {
-        if (tid == 0) { atomicOr(err, ok ? kErrCapacity : kErrFormat); *part_bytes = 0; }
+    __syncthreads();
+    const uint32_t b0 = s_b0, b1 = s_b1;
+    if (s_state) {
+        if (tid == 0) { atomicOr(err, s_state); *part_bytes = 0; }
         return;
     }
     if (tid == 0) *part_bytes = 4ull * ((uint64_t)kHdrWords + nb + 1 + (b1 - b0));
     const uint32_t *dir = stream + kHdrWords + first_block;
     for (uint64_t i = tid; i <= nb; i += stride) part[kHdrWords + i] = dir[i];
+    // payload: 16-byte loads on the (possibly remote) source side — a NVLink round trip is ~2 us, so what is in flight per
+    // thread decides the rate (4-byte loads from 300 K threads are 1.2 MB in flight: not enough for 900 GB/s) — and word
+    // stores on the local side, since source and destination are only word-aligned relative to each other
     const uint32_t *src = stream + fixed + b0;
     uint32_t *dst = part + kHdrWords + nb + 1;
     const uint64_t n = b1 - b0;
-    for (uint64_t i = tid; i < n; i += stride) dst[i] = src[i];
+    const uint64_t head = min(n, (uint64_t)((4u - (uint32_t)(((uintptr_t)src >> 2) & 3u)) & 3u));
+    const uint64_t n4 = (n - head) >> 2, tail0 = head + 4 * n4;
+    if (tid < head) dst[tid] = src[tid];
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
+    for (uint64_t i = tid; i < n4; i += stride) {
+        const uint4 v = s4[i];
+        uint32_t *d = dst + head + 4 * i;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    if (tid < n - tail0) dst[tail0 + tid] = src[tail0 + tid];
 }
 
 void launch_part_words(const unsigned long long *d_dirE, uint32_t part_blocks, unsigned long long *d_part_words_out, cudaStream_t s) {
