@@ -373,6 +373,7 @@ extern "C" int flic_encode_batch_device(flic_ctx *ctx, const uint8_t *d_pixels, 
     CU(cudaSetDevice(ctx->device));
     rc = ensure_workspace(ctx, (uint64_t)n * g.nb, staged);
     if (rc) return rc;
+    ctx->plan_valid = false;  // this call reuses the workspace a pending flic_encode_plan_device left its plan in
     cudaStream_t s = (cudaStream_t)stream;
     if (ctx->ws_used && ctx->ws_stream != s) CU(cudaStreamWaitEvent(s, ctx->ev_ws, 0));  // one workspace per context
     const uint64_t cap_words = capacity_bytes / 4;

@@ -198,7 +198,8 @@ int flic_split_finish_device(flic_ctx *ctx, uint8_t *d_part, uint32_t w, uint32_
  *                             only: positions must follow from the histograms); *d_payload_words (device) = the
  *                             part's payload size in words;
  *   (caller)                  all-gather the sizes, exclusive prefix sum -> *d_base_words (device) per GPU;
- *   flic_encode_emit_device   packs the planned part: block payloads at word 8 + total_blocks + 1 + *d_base_words +
+ *   flic_encode_emit_device   (FLIC_E_ARG unless a plan is pending: any other encode call on the context discards it)
+ *                             packs the planned part: block payloads at word 8 + total_blocks + 1 + *d_base_words +
  *                             (offset within the part) of d_stream, directory entries at word 8 + first_block + i;
  *   flic_splice_header_device (one GPU, after all parts are in: e.g. behind a tiny all-reduce) the 8 header words and
  *                             the final directory entry, from the device-side total;
